@@ -1,0 +1,159 @@
+"""Seeded synthetic inputs for the parity tests and bench.py (recipes: SURVEY.md §8d). numpy only."""
+import math
+import numpy as np
+
+
+def _horner(coeffs, x):
+    r = 0.0
+    for c in reversed(coeffs):
+        r = r * x + c
+    return r
+
+
+def _resize_bilinear_u8(src, dw, dh):
+    """Plain float bilinear upsample (half-pixel centres); only used to make a smooth synthetic background."""
+    sh, sw = src.shape
+    ys = np.clip((np.arange(dh) + 0.5) * sh / dh - 0.5, 0, sh - 1); xs = np.clip((np.arange(dw) + 0.5) * sw / dw - 0.5, 0, sw - 1)
+    y0 = np.floor(ys).astype(int); x0 = np.floor(xs).astype(int)
+    y1 = np.minimum(y0 + 1, sh - 1); x1 = np.minimum(x0 + 1, sw - 1)
+    fy = (ys - y0)[:, None]; fx = (xs - x0)[None, :]
+    s = src.astype(np.float64)
+    out = (s[y0][:, x0] * (1 - fy) * (1 - fx) + s[y0][:, x1] * (1 - fy) * fx + s[y1][:, x0] * fy * (1 - fx) + s[y1][:, x1] * fy * fx)
+    return np.rint(out).astype(np.int32)
+
+
+def fisheye_frame(cfg, frame_idx):
+    """Synthetic fisheye frame: smooth base + 400 rectangles + +-3 noise, zero outside the image circle."""
+    Iw, Ih = int(cfg["Camera.Iw"]), int(cfg["Camera.Ih"])
+    rng = np.random.default_rng(1000 + frame_idx)
+    base = _resize_bilinear_u8(rng.integers(0, 256, (Ih // 8, Iw // 8), dtype=np.uint8), Iw, Ih)
+    for _ in range(400):
+        x = int(rng.integers(0, Iw - 64)); y = int(rng.integers(0, Ih - 64))
+        w, h = (int(v) for v in rng.integers(8, 64, 2))
+        base[y:y + h, x:x + w] = int(rng.integers(0, 256))
+    base = base + rng.integers(-3, 4, (Ih, Iw))
+    img = np.clip(base, 0, 255).astype(np.uint8)
+    invp = [cfg.get("Camera.pol%d" % i, 0.0) for i in range(int(cfg["Camera.nrinvpol"]))]
+    fov = cfg["Camera.fov"] / 2.0 * math.pi / 180.0
+    theta = math.atan(-math.cos(fov) / math.sin(fov))
+    rho_max = _horner(invp, theta)
+    yy, xx = np.mgrid[0:Ih, 0:Iw]
+    img[(xx - cfg["Camera.u0"]) ** 2 + (yy - cfg["Camera.v0"]) ** 2 > rho_max ** 2] = 0
+    return img
+
+
+def descriptor_pair(pair_idx, n=2000):
+    """Config-3 pair: B = permuted A with 8 % bit flips on 70 % of rows, fresh random on 30 %."""
+    rng = np.random.default_rng(2000 + pair_idx)
+    A = rng.integers(0, 256, (n, 32), dtype=np.uint8)
+    perm = rng.permutation(n)
+    B = A[perm].copy()
+    fresh = rng.random(n) < 0.3
+    flips = np.packbits(rng.random((n, 256)) < 0.08, axis=1, bitorder="little")
+    B ^= flips
+    B[fresh] = rng.integers(0, 256, (int(fresh.sum()), 32), dtype=np.uint8)
+    angA = rng.uniform(0, 360, n).astype(np.float32)
+    angB = np.mod(angA[perm] + rng.uniform(-6, 6, n).astype(np.float32), np.float32(360)).astype(np.float32)
+    angB[angB >= 360] = 0
+    return A, angA, B, angB, perm
+
+
+# ----------------------------------------------------------------------------- bundle adjustment problem
+_FACE_TILE = {0: (1, 1), 1: (0, 1), 2: (2, 1), 3: (1, 0), 4: (1, 2)}  # face -> (col,row) of the canvas tile
+
+
+def _rays_to_cubemap(x, y, z, W):
+    """Ordered face tests of CamModelGeneral::TransformRaysToCubemap (reference src/CamModelGeneral.cpp:95-154)."""
+    f = W / 2.0
+    def proj(lx, ly, lz):
+        return lx * f / lz + f, ly * f / lz + f
+    if z > 0 and abs(x / z) <= 1 and abs(y / z) <= 1:
+        face, (u, v) = 0, proj(x, y, z)
+    elif x > 0 and abs(y / x) <= 1 and abs(z / x) <= 1:
+        face, (u, v) = 2, proj(-z, y, x)
+    elif x < 0 and abs(y / x) <= 1 and abs(z / x) <= 1:
+        face, (u, v) = 1, proj(z, y, -x)
+    elif y > 0 and abs(x / y) <= 1 and abs(z / y) <= 1:
+        face, (u, v) = 4, proj(x, -z, y)
+    elif y < 0 and abs(x / y) <= 1 and abs(z / y) <= 1:
+        face, (u, v) = 3, proj(x, z, -y)
+    else:
+        return None
+    if not (0 <= u < W and 0 <= v < W):
+        return None
+    c, r = _FACE_TILE[face]
+    return u + c * W, v + r * W
+
+
+def _rodrigues(w):
+    th = np.linalg.norm(w)
+    K = np.array([[0, -w[2], w[1]], [w[2], 0, -w[0]], [-w[1], w[0], 0]])
+    if th < 1e-12:
+        return np.eye(3) + K
+    return np.eye(3) + math.sin(th) / th * K + (1 - math.cos(th)) / th ** 2 * K @ K
+
+
+def ba_problem(nKF=50, nMP=20000, kmin=2, kmax=16, faceW=650, seed=4242, fov_deg=190.0, outlier_frac=0.05, radius=5.0):
+    """Config-4 style local BA window: KFs on a circle looking inward, points in a cube, windowed co-visibility.
+
+    Returns float32 Tcw (nKF,4,4), kf_fixed, pts (nMP,3), edges (eMP,eKF), kpxy (canvas px), inv_sigma2 and the
+    ground truth. All I/O arrays are float32 like the reference's cv::Mat boundary. radius=5 is the SURVEY §8d recipe
+    (everything lands on the front face); a radius inside the point cube (e.g. 1.5) puts observations on all 5 faces."""
+    rng = np.random.default_rng(seed)
+    cos_fov = math.cos(fov_deg / 2 * math.pi / 180)
+    Twc = []
+    for k in range(nKF):
+        a = 2 * math.pi * k / nKF
+        c = np.array([radius * math.cos(a), 0.0, radius * math.sin(a)]) + rng.uniform(-0.2, 0.2, 3)
+        zc = -c / np.linalg.norm(c)
+        up = np.array([0.0, 1.0, 0.0])
+        xc = np.cross(up, zc); xc /= np.linalg.norm(xc)
+        yc = np.cross(zc, xc)
+        R = np.stack([xc, yc, zc], 1)  # columns = camera axes in world
+        Twc.append((R, c))
+    Tcw_true = np.zeros((nKF, 4, 4))
+    for k, (R, c) in enumerate(Twc):
+        Tcw_true[k, :3, :3] = R.T; Tcw_true[k, :3, 3] = -R.T @ c; Tcw_true[k, 3, 3] = 1
+    pts_true = rng.uniform(-3, 3, (nMP, 3))
+    eMP, eKF, kp, octs = [], [], [], []
+    for l in range(nMP):
+        k = int(rng.integers(kmin, kmax + 1)); start = int(rng.integers(0, nKF))
+        for kk in sorted((start + i) % nKF for i in range(min(k, nKF))):
+            Xc = Tcw_true[kk, :3, :3] @ pts_true[l] + Tcw_true[kk, :3, 3]
+            if Xc[2] / np.linalg.norm(Xc) < cos_fov:
+                continue
+            uv = _rays_to_cubemap(Xc[0], Xc[1], Xc[2], faceW)
+            if uv is None:
+                continue
+            noise = rng.normal(0, 1, 2)
+            if rng.random() < outlier_frac:
+                noise = noise + rng.uniform(-30, 30, 2)
+            u, v = uv[0] + noise[0], uv[1] + noise[1]
+            c0, r0 = int(uv[0] // faceW), int(uv[1] // faceW)
+            u = min(max(u, c0 * faceW + 0.01), (c0 + 1) * faceW - 0.01)   # keep the observation on its face tile
+            v = min(max(v, r0 * faceW + 0.01), (r0 + 1) * faceW - 0.01)
+            eMP.append(l); eKF.append(kk); kp.append((u, v)); octs.append(int(rng.integers(0, 8)))
+    scale = np.float32(1.0); inv_sigma2_tab = []
+    for i in range(8):
+        inv_sigma2_tab.append(np.float32(1.0) / (scale * scale)); scale = scale * np.float32(1.2)
+    inv_sigma2 = np.array([inv_sigma2_tab[o] for o in octs], np.float32)
+    Tcw0 = np.zeros((nKF, 4, 4), np.float32)
+    for k in range(nKF):
+        d = rng.normal(0, 0.01, 6) if k > 0 else np.zeros(6)
+        Rn = _rodrigues(d[:3]) @ Tcw_true[k, :3, :3]
+        Tcw0[k, :3, :3] = Rn; Tcw0[k, :3, 3] = Tcw_true[k, :3, 3] + d[3:]; Tcw0[k, 3, 3] = 1
+    pts0 = (pts_true + rng.normal(0, 0.02, pts_true.shape)).astype(np.float32)
+    kf_fixed = np.zeros(nKF, np.uint8); kf_fixed[0] = 1
+    return dict(Tcw=Tcw0, kf_fixed=kf_fixed, pts=pts0, eMP=np.array(eMP, np.int32), eKF=np.array(eKF, np.int32),
+                kpxy=np.array(kp, np.float32).reshape(-1, 2), inv_sigma2=inv_sigma2, faceW=faceW, faceH=faceW,
+                Tcw_true=Tcw_true, pts_true=pts_true)
+
+
+def pose_problem(n=600, faceW=650, seed=77, outlier_frac=0.1, radius=1.5):
+    """One PoseOptimization instance: known 3-D points, noisy cubemap observations, perturbed prior pose."""
+    p = ba_problem(nKF=2, nMP=n * 3, kmin=2, kmax=2, faceW=faceW, seed=seed, outlier_frac=outlier_frac, radius=radius)
+    sel = p["eKF"] == 1
+    idx = np.nonzero(sel)[0][:n]
+    Xw = p["pts_true"][p["eMP"][idx]].astype(np.float32)
+    return dict(Tcw=p["Tcw"][1].copy(), Xw=Xw, kpxy=p["kpxy"][idx].copy(), inv_sigma2=p["inv_sigma2"][idx].copy(), faceW=faceW, faceH=faceW,
+                Tcw_true=p["Tcw_true"][1])

@@ -1,0 +1,241 @@
+"""ctypes wrapper around oracle/liboracle.so (ORACLE: test infrastructure, not product code)."""
+import ctypes as C
+import os
+import subprocess
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+KP_DTYPE = np.dtype([("x", "<f4"), ("y", "<f4"), ("size", "<f4"), ("angle", "<f4"), ("response", "<f4"),
+                     ("octave", "<i4"), ("class_id", "<i4")])
+
+
+class CamParams(C.Structure):
+    _fields_ = [("c", C.c_double), ("d", C.c_double), ("e", C.c_double), ("u0", C.c_double), ("v0", C.c_double),
+                ("p", C.c_double * 5), ("invp", C.c_double * 12), ("Iw", C.c_int), ("Ih", C.c_int),
+                ("faceW", C.c_int), ("faceH", C.c_int), ("fov", C.c_double)]
+
+
+def cam_params(cfg):
+    """cfg: dict with the reference YAML keys (Camera.*, CubeFace.*)."""
+    cp = CamParams()
+    cp.c, cp.d, cp.e = cfg["Camera.c"], cfg["Camera.d"], cfg["Camera.e"]
+    cp.u0, cp.v0 = cfg["Camera.u0"], cfg["Camera.v0"]
+    for i in range(5):
+        cp.p[i] = cfg.get("Camera.a%d" % i, 0.0) if i < int(cfg["Camera.nrpol"]) else 0.0
+    for i in range(12):
+        cp.invp[i] = cfg.get("Camera.pol%d" % i, 0.0) if i < int(cfg["Camera.nrinvpol"]) else 0.0
+    cp.Iw, cp.Ih = int(cfg["Camera.Iw"]), int(cfg["Camera.Ih"])
+    cp.faceW, cp.faceH = int(cfg["CubeFace.w"]), int(cfg["CubeFace.h"])
+    cp.fov = cfg["Camera.fov"]
+    return cp
+
+
+def build():
+    subprocess.check_call(["make", "-s", "-C", _HERE, "liboracle.so"])
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        path = os.path.join(_HERE, "liboracle.so")
+        if not os.path.exists(path):
+            build()
+        _LIB = C.CDLL(path)
+        _LIB.orc_orb_create.restype = C.c_void_p
+        _LIB.orc_warp_extract_batch.restype = C.c_long
+    return _LIB
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def _u8(a):
+    return np.ascontiguousarray(a, dtype=np.uint8)
+
+
+def _f32(a):
+    return np.ascontiguousarray(a, dtype=np.float32)
+
+
+def _i32(a):
+    return np.ascontiguousarray(a, dtype=np.int32)
+
+
+# ----------------------------------------------------------------------------- primitives
+def remap_bilinear(src, mapx, mapy):
+    src = _u8(src); mapx = _f32(mapx); mapy = _f32(mapy)
+    dst = np.empty(mapx.shape, np.uint8)
+    lib().orc_remap_bilinear(_p(src), src.shape[1], src.shape[0], _p(mapx), _p(mapy), _p(dst), mapx.shape[1], mapx.shape[0])
+    return dst
+
+
+def resize_linear(src, dw, dh):
+    src = _u8(src); dst = np.empty((dh, dw), np.uint8)
+    lib().orc_resize_linear(_p(src), src.shape[1], src.shape[0], _p(dst), dw, dh)
+    return dst
+
+
+def fast(img, thr):
+    img = _u8(img); cap = img.size
+    out = np.empty((cap, 3), np.int32)
+    n = lib().orc_fast(_p(img), img.shape[1], img.shape[0], int(thr), _p(out), cap)
+    return out[:n].copy()
+
+
+def gaussian7(img):
+    img = _u8(img); dst = np.empty_like(img)
+    lib().orc_gaussian7(_p(img), img.shape[1], img.shape[0], _p(dst))
+    return dst
+
+
+def fast_atan2(y, x):
+    y = _f32(y); x = _f32(x); out = np.empty_like(y)
+    lib().orc_fast_atan2(_p(y), _p(x), _p(out), y.size)
+    return out
+
+
+def sincos(a):
+    a = _f32(a); s = np.empty_like(a); c = np.empty_like(a)
+    lib().orc_sincos(_p(a), _p(s), _p(c), a.size)
+    return s, c
+
+
+# ----------------------------------------------------------------------------- warp
+def build_maps(cp):
+    W3, H3 = 3 * cp.faceW, 3 * cp.faceH
+    m1 = np.empty((H3, W3), np.float32); m2 = np.empty((H3, W3), np.float32)
+    lib().orc_build_maps(C.byref(cp), _p(m1), _p(m2))
+    return m1, m2
+
+
+def cubemap_to_fisheye(cp, up, vp):
+    uf = C.c_double(); vf = C.c_double()
+    lib().orc_cubemap_to_fisheye(C.byref(cp), C.c_double(up), C.c_double(vp), C.byref(uf), C.byref(vf))
+    return uf.value, vf.value
+
+
+def warp(cp, fisheye, m1, m2, canvas=None):
+    fisheye = _u8(fisheye)
+    assert fisheye.shape == (cp.Ih, cp.Iw)
+    if canvas is None:
+        canvas = np.zeros((3 * cp.faceH, 3 * cp.faceW), np.uint8)
+    lib().orc_warp(C.byref(cp), _p(fisheye), _p(m1), _p(m2), _p(canvas))
+    return canvas
+
+
+# ----------------------------------------------------------------------------- extractor
+class ORBextractor:
+    def __init__(self, nfeatures, scaleFactor, nlevels, iniThFAST, minThFAST, faceW, faceH):
+        self.nlevels = nlevels
+        self.nfeatures = nfeatures
+        self._h = C.c_void_p(lib().orc_orb_create(int(nfeatures), C.c_float(scaleFactor), int(nlevels), int(iniThFAST),
+                                                  int(minThFAST), int(faceW), int(faceH)))
+        sc = [np.empty(nlevels, np.float32) for _ in range(4)]
+        per = np.empty(nlevels, np.int32); um = np.empty(16, np.int32)
+        lib().orc_orb_tables(self._h, _p(sc[0]), _p(sc[1]), _p(sc[2]), _p(sc[3]), _p(per), _p(um))
+        self.scale, self.inv_scale, self.sigma2, self.inv_sigma2 = sc
+        self.features_per_level, self.umax = per, um
+
+    def __del__(self):
+        try:
+            lib().orc_orb_destroy(self._h)
+        except Exception:
+            pass
+
+    def __call__(self, image, mask):
+        image = _u8(image); mask = _u8(mask)
+        assert image.shape == mask.shape
+        n = lib().orc_orb_extract(self._h, _p(image), image.shape[1], image.shape[0], _p(mask))
+        kps = np.empty(n, KP_DTYPE); desc = np.empty((n, 32), np.uint8)
+        lib().orc_orb_result(self._h, _p(kps), _p(desc))
+        return kps, desc
+
+    def level_image(self, level, blurred=False):
+        w = C.c_int(); h = C.c_int()
+        lib().orc_orb_level_size(self._h, level, C.byref(w), C.byref(h))
+        out = np.zeros((h.value, w.value), np.uint8)
+        lib().orc_orb_level_image(self._h, level, int(blurred), _p(out))
+        return out
+
+    def stage(self, level, stage):
+        """stage 0: FAST-grid candidates (minBorder-relative); 1: after distribution + orientation (level coords)."""
+        n = lib().orc_orb_stage_count(self._h, level, stage)
+        out = np.empty(n, KP_DTYPE)
+        lib().orc_orb_stage_get(self._h, level, stage, _p(out))
+        return out
+
+
+def warp_extract_batch(cp, fisheyes, m1, m2, mask, nfeatures, scaleFactor, nlevels, iniTh, minTh, nthreads):
+    fisheyes = _u8(fisheyes); mask = _u8(mask)
+    return lib().orc_warp_extract_batch(C.byref(cp), _p(fisheyes), fisheyes.shape[0], _p(m1), _p(m2), _p(mask), int(nfeatures),
+                                        C.c_float(scaleFactor), int(nlevels), int(iniTh), int(minTh), int(nthreads))
+
+
+# ----------------------------------------------------------------------------- matcher
+def descriptor_distance(a, b):
+    a = _u8(a); b = _u8(b)
+    return lib().orc_descriptor_distance(_p(a), _p(b))
+
+
+def search_by_bow(descKF, angKF, kfValid, nodeKF, descF, angF, nodeF, nnratio=0.7, checkOri=True):
+    descKF = _u8(descKF); descF = _u8(descF); angKF = _f32(angKF); angF = _f32(angF)
+    kfValid = _u8(kfValid); nodeKF = _i32(nodeKF); nodeF = _i32(nodeF)
+    matchF = np.empty(descF.shape[0], np.int32)
+    n = lib().orc_search_by_bow(_p(descKF), _p(angKF), _p(kfValid), _p(nodeKF), descKF.shape[0], _p(descF), _p(angF), _p(nodeF),
+                                descF.shape[0], C.c_float(nnratio), int(checkOri), _p(matchF))
+    return n, matchF
+
+
+def match_bruteforce(descA, angA, descB, angB, nnratio=0.6, thLow=50, checkOri=True):
+    descA = _u8(descA); descB = _u8(descB); angA = _f32(angA); angB = _f32(angB)
+    nA = descA.shape[0]
+    m = np.empty(nA, np.int32); d = np.empty(nA, np.int32); s = np.empty(nA, np.int32)
+    n = lib().orc_match_bruteforce(_p(descA), _p(angA), nA, _p(descB), _p(angB), descB.shape[0], C.c_float(nnratio), int(thLow),
+                                   int(checkOri), _p(m), _p(d), _p(s))
+    return n, m, d, s
+
+
+def match_bruteforce_batch(descA, angA, descB, angB, nnratio=0.6, thLow=50, checkOri=True, nthreads=1):
+    descA = _u8(descA); descB = _u8(descB); angA = _f32(angA); angB = _f32(angB)
+    P, nA = descA.shape[0], descA.shape[1]
+    m = np.empty((P, nA), np.int32); nm = np.empty(P, np.int32)
+    lib().orc_match_bruteforce_batch(_p(descA), _p(angA), nA, _p(descB), _p(angB), descB.shape[1], P, C.c_float(nnratio), int(thLow),
+                                     int(checkOri), _p(m), _p(nm), int(nthreads))
+    return nm, m
+
+
+# ----------------------------------------------------------------------------- bundle adjustment
+def local_ba(Tcw, kf_fixed, pts, eMP, eKF, kpxy, inv_sigma2, faceW, faceH, its1=5, its2=10, stop_flag=None):
+    Tcw = _f32(Tcw).copy(); pts = _f32(pts).copy()
+    kf_fixed = _u8(kf_fixed); eMP = _i32(eMP); eKF = _i32(eKF); kpxy = _f32(kpxy); inv_sigma2 = _f32(inv_sigma2)
+    nKF, nMP, nE = Tcw.shape[0], pts.shape[0], eMP.shape[0]
+    outlier = np.zeros(nE, np.uint8); pose64 = np.zeros((nKF, 7)); pts64 = np.zeros((nMP, 3)); log = np.zeros((64, 4))
+    sf = _p(stop_flag) if stop_flag is not None else None
+    n = lib().orc_local_ba(nKF, nMP, nE, _p(Tcw), _p(kf_fixed), _p(pts), _p(eMP), _p(eKF), _p(kpxy), _p(inv_sigma2), int(faceW), int(faceH),
+                           sf, int(its1), int(its2), _p(outlier), _p(pose64), _p(pts64), _p(log), 64)
+    return dict(Tcw=Tcw.reshape(nKF, 4, 4), pts=pts, outlier=outlier, pose64=pose64, pts64=pts64, log=log[:n], iters=n)
+
+
+def pose_opt(Tcw, Xw, kpxy, inv_sigma2, faceW, faceH):
+    Tcw = _f32(Tcw).copy().reshape(16); Xw = _f32(Xw); kpxy = _f32(kpxy); inv_sigma2 = _f32(inv_sigma2)
+    n = Xw.shape[0]
+    outlier = np.zeros(max(n, 1), np.uint8); pose64 = np.zeros(7); log = np.zeros((64, 4)); nit = C.c_int()
+    inl = lib().orc_pose_opt(n, _p(Tcw), _p(Xw), _p(kpxy), _p(inv_sigma2), int(faceW), int(faceH), _p(outlier), _p(pose64), _p(log), 64,
+                             C.byref(nit))
+    return dict(inliers=inl, Tcw=Tcw.reshape(4, 4), outlier=outlier[:n], pose64=pose64, log=log[:nit.value])
+
+
+def se3_exp(u):
+    u = np.ascontiguousarray(u, np.float64); out = np.zeros(7)
+    lib().orc_se3_exp(_p(u), _p(out))
+    return out
+
+
+def edge_eval(Tcw, X, kx, ky, faceW, faceH):
+    Tcw = _f32(Tcw).reshape(16); X = np.ascontiguousarray(X, np.float64)
+    err = np.zeros(2); Jp = np.zeros((2, 6)); Jx = np.zeros((2, 3)); face = C.c_int()
+    lib().orc_edge_eval(_p(Tcw), _p(X), C.c_float(kx), C.c_float(ky), int(faceW), int(faceH), _p(err), _p(Jp), _p(Jx), C.byref(face))
+    return err, Jp, Jx, face.value
