@@ -1,0 +1,1014 @@
+// Front end of libcubemap_b200.so: fisheye->cubemap warp + ORB extraction, batched, sm_100a.
+//
+// Reference path (CPU, one frame at a time):
+//   System::CvtFisheyeToCubeMap_reverseQuery_withInterpolation   src/System.cpp:327-355   (5 x cv::remap)
+//   ORBextractor::operator()                                      src/ORBExtractor.cpp:838-926
+//     ComputePyramid :928-953, ComputeKeyPointsOctTree :739-827 (cv::FAST per 30-px cell, DistributeOctTree
+//     :511-737, IC_Angle :48-75), cull :883-904, GaussianBlur :907-908, computeOrbDescriptor :79-118
+//
+// Kernels (all HBM/L2-bound byte work; no tensor cores on this path):
+//   k_warp        canvas face tiles <- bilinear gather of the fisheye frame through a pre-quantised map
+//   k_pyramid     level l <- cv::resize(INTER_LINEAR) fixed-point model of level l-1
+//   k_fast        per 30-px cell FAST-9/16 arc score, in-cell NMS, 20->7 threshold fallback, candidate append
+//   k_distribute  the reference's quadtree, restated as data-parallel rounds over nodes
+//   k_describe    IC angle + 7x7 Gaussian of the 43x43 neighbourhood + steered BRIEF, one warp per keypoint
+#include <cmath>
+#include <cstring>
+#include <vector>
+#include "common.cuh"
+
+namespace cslam {
+
+static const int PATCH_SIZE = 31, HALF_PATCH = 15, EDGE_THRESHOLD = 19;
+static const int MAX_LEVELS = 16;
+static const int CG = 4;            // cells per CTA (x) in k_fast
+static const int CELL_MAX = 48;     // largest supported cell edge
+static const int FAST_TS = 208;     // smem tile stride (bytes), >= CG*CELL_MAX+6+3 rounded
+static const int FAST_TH = CELL_MAX + 6;
+static const int DESC_WARPS = 4;
+
+__constant__ signed char c_pattern[1024] = {
+#include "brief_pattern.inc"
+};
+__constant__ int c_umax[16];
+
+struct LevelGeom {
+    int w, h, pitch;          // image size, row pitch in bytes
+    int minB, maxBX, maxBY;   // FAST region (EDGE_THRESHOLD-3 inset)
+    int wCell, hCell, nColsEff, nRowsEff;
+    int quota;                // mnFeaturesPerLevel
+    int candCap;
+    float scale;              // mvScaleFactor
+    float sizeF;              // (int)(PATCH_SIZE*scale)
+};
+
+struct DevLevels {
+    LevelGeom g[MAX_LEVELS];
+    uint8_t* img[MAX_LEVELS];          // batch-major: frame f at img + f*pitch*h
+    uint32_t* cand[MAX_LEVELS];        // batch x candCap packed (x | y<<12 | resp<<24), minBorder-relative
+    uint16_t* pnode[MAX_LEVELS];       // batch x candCap scratch for k_distribute
+    const uint16_t* xofs[MAX_LEVELS];  // resize tables for building level l from l-1
+    const uint32_t* xab[MAX_LEVELS];   // a0 | a1<<16
+    const uint16_t* yofs[MAX_LEVELS];
+    const uint32_t* yab[MAX_LEVELS];
+    int nlevels;
+};
+
+// ------------------------------------------------------------------------------------------------- k_warp
+// Map entry: sx | sy<<16 with sx=cvRound(u*32), sy=cvRound(v*32) (cv::remap's INTER_BITS=5 fixed point).
+// Weights are exact integers: (32-fy)(32-fx)*32 etc. (= cvRound of the fp32 table products * 32768).
+// One thread = one canvas pixel of one face row, looped over FPT frames so a map entry is read once per FPT frames.
+template <int FPT>
+__global__ void __launch_bounds__(256) k_warp(const uint8_t* __restrict__ fisheye, int Iw, int Ih, const uint32_t* __restrict__ map, int W,
+                                              uint8_t* __restrict__ canvas, int cpitch, size_t cframe, int batch) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    const int row = blockIdx.y;
+    const int face = blockIdx.z % 5, fg = blockIdx.z / 5;
+    if (x >= W) return;
+    const int tcol = (face == 1) ? 0 : (face == 2) ? 2 : 1;
+    const int trow = (face == 3) ? 0 : (face == 4) ? 2 : 1;
+    const uint32_t m = __ldg(map + ((size_t)face * W + row) * W + x);
+    const int sx = m & 0xffff, sy = m >> 16;
+    const int ix = sx >> 5, iy = sy >> 5, fx = sx & 31, fy = sy & 31;
+    const int w00 = (32 - fy) * (32 - fx) * 32, w01 = (32 - fy) * fx * 32, w10 = fy * (32 - fx) * 32, w11 = fy * fx * 32;
+    // ix,iy >= 0 always (maps are >= 0); each tap outside the source reads 0 (BORDER_CONSTANT)
+    const bool x0ok = ix < Iw, x1ok = ix + 1 < Iw, y0ok = iy < Ih, y1ok = iy + 1 < Ih;
+    const size_t o00 = (size_t)iy * Iw + ix;
+    const size_t dst = (size_t)(trow * W + row) * cpitch + tcol * W + x;
+#pragma unroll
+    for (int k = 0; k < FPT; k++) {
+        const int f = fg * FPT + k;
+        if (f >= batch) break;
+        const uint8_t* S = fisheye + (size_t)f * Iw * Ih;
+        int v = 0;
+        if (y0ok) {
+            if (x0ok) v += __ldg(S + o00) * w00;
+            if (x1ok) v += __ldg(S + o00 + 1) * w01;
+        }
+        if (y1ok) {
+            if (x0ok) v += __ldg(S + o00 + Iw) * w10;
+            if (x1ok) v += __ldg(S + o00 + Iw + 1) * w11;
+        }
+        canvas[(size_t)f * cframe + dst] = (uint8_t)((v + (1 << 14)) >> 15);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------- k_pyramid
+// cv::resize(src,dst,sz,0,0,INTER_LINEAR) 8U model: 11-bit coefficients, horizontal int pass, vertical
+// (((b0*(r0>>4))>>16)+((b1*(r1>>4))>>16)+2)>>2.  One thread = 4 consecutive dst pixels (one u32 store).
+__global__ void __launch_bounds__(256) k_pyramid(const uint8_t* __restrict__ src, int sw, int sh, int spitch, uint8_t* __restrict__ dst, int dw, int dh,
+                                                 int dpitch, const uint16_t* __restrict__ xofs, const uint32_t* __restrict__ xab,
+                                                 const uint16_t* __restrict__ yofs, const uint32_t* __restrict__ yab) {
+    const int x4 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    const int y = blockIdx.y;
+    if (x4 >= dw) return;
+    const uint8_t* S = src + (size_t)blockIdx.z * spitch * sh;
+    uint8_t* D = dst + (size_t)blockIdx.z * dpitch * dh;
+    const int sy0 = yofs[y], sy1 = min(sy0 + 1, sh - 1);
+    const uint32_t bb = yab[y];
+    const int b0 = (int)(bb & 0xffff), b1 = (int)(bb >> 16);
+    const uint8_t* R0 = S + (size_t)sy0 * spitch;
+    const uint8_t* R1 = S + (size_t)sy1 * spitch;
+    uint32_t out = 0;
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        const int x = x4 + k;
+        if (x < dw) {
+            const int s0 = xofs[x], s1 = min(s0 + 1, sw - 1);
+            const uint32_t aa = xab[x];
+            const int a0 = (int)(aa & 0xffff), a1 = (int)(aa >> 16);
+            const int r0 = __ldg(R0 + s0) * a0 + __ldg(R0 + s1) * a1;
+            const int r1 = __ldg(R1 + s0) * a0 + __ldg(R1 + s1) * a1;
+            int v = (((b0 * (r0 >> 4)) >> 16) + ((b1 * (r1 >> 4)) >> 16) + 2) >> 2;
+            v = min(max(v, 0), 255);
+            out |= (uint32_t)v << (8 * k);
+        }
+    }
+    *reinterpret_cast<uint32_t*>(D + (size_t)y * dpitch + x4) = out;   // pitch is a multiple of 128: padding absorbs the tail
+}
+
+// ------------------------------------------------------------------------------------------------- k_fast
+// Arc score s(p) = max over the 16 arcs of 9 contiguous ring pixels of max(min(d), min(-d)), d = p - ring.
+// corner(thr) <=> s > thr; OpenCV response = s-1. The reference runs cv::FAST per cell ROI [ini, ini+cell+6):
+// detection areas of neighbouring cells tile the level without overlap, NMS only sees scores of the same cell,
+// and the 20->7 fallback is decided per cell on "no keypoint survived NMS" (src/ORBExtractor.cpp:763-803).
+__device__ __forceinline__ int arc9_mask(uint32_t m) {   // m: 16-bit ring mask; non-zero iff 9 contiguous bits (cyclic)
+    m |= m << 16;
+    uint32_t a = m & (m >> 1);
+    a &= a >> 2;
+    a &= a >> 4;
+    a &= m >> 8;
+    return a & 0xffff;
+}
+
+__device__ __forceinline__ int fast_score(const uint8_t* t, int minTh) {
+    // ring offsets clockwise from (0,-3)
+    const int c = t[0];
+    int d[16];
+    d[0] = c - t[-3 * FAST_TS + 0];  d[1] = c - t[-3 * FAST_TS + 1];  d[2] = c - t[-2 * FAST_TS + 2];  d[3] = c - t[-1 * FAST_TS + 3];
+    d[4] = c - t[3];                 d[5] = c - t[1 * FAST_TS + 3];   d[6] = c - t[2 * FAST_TS + 2];   d[7] = c - t[3 * FAST_TS + 1];
+    d[8] = c - t[3 * FAST_TS + 0];   d[9] = c - t[3 * FAST_TS - 1];   d[10] = c - t[2 * FAST_TS - 2];  d[11] = c - t[1 * FAST_TS - 3];
+    d[12] = c - t[-3];               d[13] = c - t[-1 * FAST_TS - 3]; d[14] = c - t[-2 * FAST_TS - 2]; d[15] = c - t[-3 * FAST_TS - 1];
+    uint32_t hi = 0, lo = 0;
+#pragma unroll
+    for (int k = 0; k < 16; k++) { hi |= (uint32_t)(d[k] > minTh) << k; lo |= (uint32_t)(d[k] < -minTh) << k; }
+    if (!arc9_mask(hi) && !arc9_mask(lo)) return 0;
+    // exact score: sliding min/max over 9 contiguous (doubling: 2,4,8,+1)
+    int mn[16], mx[16];
+#pragma unroll
+    for (int k = 0; k < 16; k++) { mn[k] = min(d[k], d[(k + 1) & 15]); mx[k] = max(d[k], d[(k + 1) & 15]); }
+    int mn4[16], mx4[16];
+#pragma unroll
+    for (int k = 0; k < 16; k++) { mn4[k] = min(mn[k], mn[(k + 2) & 15]); mx4[k] = max(mx[k], mx[(k + 2) & 15]); }
+    int best = 0;
+#pragma unroll
+    for (int k = 0; k < 16; k++) {
+        const int a = min(min(mn4[k], mn4[(k + 4) & 15]), d[(k + 8) & 15]);
+        const int b = max(max(mx4[k], mx4[(k + 4) & 15]), d[(k + 8) & 15]);
+        best = max(best, max(a, -b));
+    }
+    return best;
+}
+
+__global__ void __launch_bounds__(256) k_fast(const uint8_t* __restrict__ img, LevelGeom g, int iniTh, int minTh, uint32_t* __restrict__ cand,
+                                              uint32_t* __restrict__ candCount, int countStride, int* __restrict__ errFlag) {
+    __shared__ __align__(16) uint8_t tile[FAST_TH * FAST_TS];
+    __shared__ uint8_t S[(CELL_MAX + 2) * (CG * CELL_MAX + 2)];
+    __shared__ int cnt20[CG];
+    __shared__ int anyNonZero;
+    const int frame = blockIdx.z, cellRow = blockIdx.y, j0 = blockIdx.x * CG;
+    const int tid = threadIdx.x;
+    const uint8_t* I = img + (size_t)frame * g.pitch * g.h;
+    const int iniY = g.minB + cellRow * g.hCell, maxY = min(iniY + g.hCell + 6, g.maxBY);
+    const int ncell = min(CG, g.nColsEff - j0);
+    const int tx0 = g.minB + j0 * g.wCell, tx1 = min(tx0 + ncell * g.wCell + 6, g.maxBX);
+    const int a0 = tx0 & ~3, nwords = (tx1 - a0 + 3) >> 2, nrows = maxY - iniY;
+    if (tid < CG) cnt20[tid] = 0;
+    if (tid == 0) anyNonZero = 0;
+    __syncthreads();
+    uint32_t acc = 0;
+    for (int i = tid; i < nwords * nrows; i += blockDim.x) {
+        const int r = i / nwords, wd = i - r * nwords;
+        const uint32_t v = __ldg(reinterpret_cast<const uint32_t*>(I + (size_t)(iniY + r) * g.pitch + a0) + wd);
+        *reinterpret_cast<uint32_t*>(tile + r * FAST_TS + wd * 4) = v;
+        acc |= v;
+    }
+    if (acc) anyNonZero = 1;
+    __syncthreads();
+    if (!anyNonZero) return;   // an all-zero tile (black cubemap corner) has no corners at any threshold
+    const int nx = tx1 - tx0 - 6, ny = nrows - 6;   // detection area
+    if (nx <= 0 || ny <= 0) return;
+    const int SS = nx + 2;
+    for (int i = tid; i < SS * (ny + 2); i += blockDim.x) {
+        const int yy = i / SS, xx = i - yy * SS;
+        if (yy == 0 || yy == ny + 1 || xx == 0 || xx == nx + 1) S[i] = 0;
+    }
+    const int xoff = tx0 - a0 + 3;
+    for (int i = tid; i < nx * ny; i += blockDim.x) {
+        const int y = i / nx, x = i - y * nx;
+        S[(y + 1) * SS + x + 1] = (uint8_t)fast_score(tile + (y + 3) * FAST_TS + xoff + x, minTh);
+    }
+    __syncthreads();
+    // keypoint test for threshold T: s > T and no same-cell neighbour n with s_n > T and s_n >= s
+    auto is_kp = [&](int x, int y, int T) -> bool {
+        const uint8_t* c = S + (y + 1) * SS + x + 1;
+        const int s = c[0];
+        if (s <= T) return false;
+        const int xl = x % g.wCell;
+        const bool lok = xl != 0, rok = (xl != g.wCell - 1);
+        int m = max(c[-SS], c[SS]);
+        if (lok) m = max(m, max(c[-1], max(c[-SS - 1], c[SS - 1])));
+        if (rok) m = max(m, max(c[1], max(c[-SS + 1], c[SS + 1])));
+        return !(m > T && m >= s);
+    };
+    for (int i = tid; i < nx * ny; i += blockDim.x) {
+        const int y = i / nx, x = i - y * nx;
+        if (is_kp(x, y, iniTh)) atomicAdd(&cnt20[x / g.wCell], 1);
+    }
+    __syncthreads();
+    uint32_t* out = cand + (size_t)frame * g.candCap;
+    uint32_t* cc = candCount + (size_t)frame * countStride;
+    const int niter = (nx * ny + blockDim.x - 1) / blockDim.x;
+    for (int it = 0; it < niter; it++) {
+        const int i = it * blockDim.x + tid;
+        bool kp = false; int x = 0, y = 0;
+        if (i < nx * ny) {
+            y = i / nx; x = i - y * nx;
+            kp = is_kp(x, y, cnt20[x / g.wCell] > 0 ? iniTh : minTh);
+        }
+        const unsigned ball = __ballot_sync(0xffffffffu, kp);
+        if (ball) {
+            const int lane = tid & 31, leader = __ffs(ball) - 1;
+            uint32_t base = 0;
+            if (lane == leader) base = atomicAdd(cc, __popc(ball));
+            base = __shfl_sync(0xffffffffu, base, leader);
+            if (kp) {
+                const uint32_t pos = base + __popc(ball & ((1u << lane) - 1));
+                if (pos < (uint32_t)g.candCap) {
+                    const uint32_t X = tx0 + 3 + x - g.minB, Y = iniY + 3 + y - g.minB;
+                    out[pos] = X | (Y << 12) | ((uint32_t)(S[(y + 1) * SS + x + 1] - 1) << 24);
+                } else {
+                    *errFlag = CSLAM_E_CAPACITY;
+                }
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------- k_distribute
+// DistributeOctTree (src/ORBExtractor.cpp:511-737) without lists or pointers. Facts used:
+//  * children bounds depend only on the parent bounds; a key's child is decided by x<midX / y<midY;
+//  * std::list::push_front everywhere => list order == descending creation sequence, so "list order" is a sort key;
+//  * the order of keys inside a node only matters for the final "max response, first wins" pick, and the first key
+//    of equal response is the one earliest in (cell row, cell col, y, x) order, recoverable from coordinates.
+// One CTA per (level, frame). Nodes live in shared memory, keys stay in global/L2 with a per-key node index.
+struct QNode { uint16_t ulx, uly, brx, bry; uint32_t cnt; uint32_t seq : 31; uint32_t flagE : 1; };
+
+__device__ __forceinline__ uint32_t block_exclusive_scan(uint32_t* data, int n, uint32_t* warpSums) {
+    // in-place exclusive scan of data[0..n) by the whole block; returns the total. n <= blockDim.x * per
+    const int T = blockDim.x, tid = threadIdx.x;
+    const int per = (n + T - 1) / T;
+    const int lo = min(tid * per, n), hi = min(lo + per, n);
+    uint32_t s = 0;
+    for (int i = lo; i < hi; i++) s += data[i];
+    // block scan of s
+    const int lane = tid & 31, wid = tid >> 5;
+    uint32_t v = s;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { uint32_t t = __shfl_up_sync(0xffffffffu, v, o); if (lane >= o) v += t; }
+    if (lane == 31) warpSums[wid] = v;
+    __syncthreads();
+    if (wid == 0) {
+        uint32_t w = lane < (T >> 5) ? warpSums[lane] : 0;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { uint32_t t = __shfl_up_sync(0xffffffffu, w, o); if (lane >= o) w += t; }
+        warpSums[lane] = w;
+    }
+    __syncthreads();
+    uint32_t excl = v - s + (wid ? warpSums[wid - 1] : 0);
+    const uint32_t total = warpSums[(T >> 5) - 1];
+    for (int i = lo; i < hi; i++) { uint32_t t = data[i]; data[i] = excl; excl += t; }
+    __syncthreads();
+    return total;
+}
+
+struct DistributeArgs {
+    DevLevels L;
+    const uint32_t* candCount;   // batch x nlevels
+    uint32_t* kept;              // batch x nlevels x keptCap : x | y<<12 | resp<<24 in LEVEL coordinates
+    uint32_t* keptCount;         // batch x nlevels
+    const uint8_t* mask; int maskPitch; int imgW, imgH, faceW, faceH;
+    int keptCap, M;              // M: node capacity
+    int* errFlag;
+};
+
+__global__ void __launch_bounds__(256) k_distribute(DistributeArgs A) {
+    extern __shared__ __align__(16) uint8_t smem_raw[];
+    const int level = blockIdx.x, frame = blockIdx.y, tid = threadIdx.x, T = blockDim.x;
+    const LevelGeom g = A.L.g[level];
+    const int M = A.M, N = g.quota;
+    QNode* listA = reinterpret_cast<QNode*>(smem_raw);
+    QNode* listB = listA + M;
+    uint32_t* childCnt = reinterpret_cast<uint32_t*>(listB + M);   // M*4 (count, later new position)
+    uint32_t* scanA = childCnt + 4 * M;                            // M
+    uint32_t* scanB = scanA + M;                                   // M
+    uint16_t* ordOf = reinterpret_cast<uint16_t*>(scanB + M);      // M  processing order of a split node
+    uint16_t* remap = ordOf + M;                                   // M
+    uint8_t* splitF = reinterpret_cast<uint8_t*>(remap + M);       // M
+    __shared__ uint32_t warpSums[32];
+    __shared__ int sh_nToExpand, sh_J;
+    __shared__ uint32_t sh_base;
+
+    const uint32_t nAll = A.candCount[(size_t)frame * A.L.nlevels + level];
+    const int n = (int)min(nAll, (uint32_t)g.candCap);
+    const uint32_t* pts = A.L.cand[level] + (size_t)frame * g.candCap;
+    uint16_t* pnode = A.L.pnode[level] + (size_t)frame * g.candCap;
+    uint32_t* keptOut = A.kept + ((size_t)frame * A.L.nlevels + level) * A.keptCap;
+    uint32_t* keptCnt = A.keptCount + (size_t)frame * A.L.nlevels + level;
+    if (n == 0) { if (tid == 0) *keptCnt = 0; return; }
+
+    QNode* cur = listA; QNode* nxt = listB;
+    if (tid == 0) {
+        QNode r; r.ulx = 0; r.uly = 0; r.brx = (uint16_t)(g.maxBX - g.minB); r.bry = (uint16_t)(g.maxBY - g.minB);
+        r.cnt = (uint32_t)n; r.flagE = 0; r.seq = 0;
+        cur[0] = r;
+    }
+    for (int p = tid; p < n; p += T) pnode[p] = 0;
+    __syncthreads();
+    int nList = 1; uint32_t seqNext = 1; bool finishMode = false;
+
+    for (int round = 0; round < 64; round++) {
+        const int prevSize = nList;
+        // ---- which nodes are candidates to split, and in which order
+        int nCandSplit = 0;
+        if (!finishMode) {
+            for (int i = tid; i < nList; i += T) scanA[i] = cur[i].cnt > 1 ? 1u : 0u;
+            __syncthreads();
+            for (int i = tid; i < nList; i += T) splitF[i] = (uint8_t)scanA[i];
+            __syncthreads();
+            nCandSplit = (int)block_exclusive_scan(scanA, nList, warpSums);
+            for (int i = tid; i < nList; i += T) ordOf[i] = (uint16_t)scanA[i];
+        } else {
+            // rank expandable nodes by descending (count, seq): the reference sorts ascending and walks from the back
+            for (int i = tid; i < nList; i += T) {
+                int r = 0; const bool e = cur[i].flagE != 0;
+                if (e) {
+                    const uint32_t ci = cur[i].cnt, si = cur[i].seq;
+                    for (int k = 0; k < nList; k++) {
+                        if (!cur[k].flagE) continue;
+                        const uint32_t ck = cur[k].cnt, sk = cur[k].seq;
+                        r += (ck > ci) || (ck == ci && sk > si);
+                    }
+                }
+                splitF[i] = e; ordOf[i] = (uint16_t)r; scanA[i] = e;
+            }
+            __syncthreads();
+            nCandSplit = (int)block_exclusive_scan(scanA, nList, warpSums);
+        }
+        if (nCandSplit == 0) break;   // nothing can be divided (the reference would spin forever here)
+        // ---- children populations
+        for (int i = tid; i < 4 * nList; i += T) childCnt[i] = 0;
+        __syncthreads();
+        for (int p = tid; p < n; p += T) {
+            const int i = pnode[p];
+            if (splitF[i]) {
+                const QNode nd = cur[i];
+                const uint32_t v = pts[p];
+                const int x = v & 0xfff, y = (v >> 12) & 0xfff;
+                const int midX = nd.ulx + ((nd.brx - nd.ulx + 1) >> 1), midY = nd.uly + ((nd.bry - nd.uly + 1) >> 1);
+                atomicAdd(&childCnt[4 * i + (x < midX ? 0 : 1) + (y < midY ? 0 : 2)], 1u);
+            }
+        }
+        __syncthreads();
+        // ---- finishing phase: stop after the split that makes the list reach N
+        int nSplit = nCandSplit;
+        if (finishMode) {
+            for (int i = tid; i < nCandSplit; i += T) scanB[i] = 0;
+            __syncthreads();
+            for (int i = tid; i < nList; i += T) if (splitF[i]) {
+                int k = 0;
+                for (int q = 0; q < 4; q++) k += childCnt[4 * i + q] > 0;
+                scanB[ordOf[i]] = (uint32_t)(k - 1);
+            }
+            if (tid == 0) sh_J = nCandSplit;
+            __syncthreads();
+            block_exclusive_scan(scanB, nCandSplit, warpSums);
+            // scanB[o] = growth before processing o; size after o = prevSize + scanB[o] + gain(o) = prevSize + scanB[o+1]
+            for (int o = tid; o < nCandSplit; o += T) {
+                const uint32_t before = prevSize + scanB[o];
+                // size after processing o >= N  <=>  the first o whose "before" is < N but after >= N
+                // after(o) = before(o+1) for o+1 < nCandSplit; handle the last one by recomputing its gain below
+                if (before >= (uint32_t)N) atomicMin(&sh_J, o);   // o-1 was the breaking split => splits = o
+            }
+            __syncthreads();
+            nSplit = sh_J;   // number of nodes actually divided (those with ord < nSplit)
+            __syncthreads();
+            for (int i = tid; i < nList; i += T) if (splitF[i] && ordOf[i] >= nSplit) splitF[i] = 0;
+            __syncthreads();
+        }
+        // ---- creation ranks of children (reference creation order = processing order, n1..n4)
+        for (int i = tid; i < nSplit; i += T) scanB[i] = 0;
+        __syncthreads();
+        for (int i = tid; i < nList; i += T) {
+            if (splitF[i]) {
+                int k = 0;
+                for (int q = 0; q < 4; q++) k += childCnt[4 * i + q] > 0;
+                scanB[ordOf[i]] = (uint32_t)k;
+            }
+            scanA[i] = splitF[i] ? 0u : 1u;
+        }
+        __syncthreads();
+        const int C = (int)block_exclusive_scan(scanB, nSplit, warpSums);
+        const int nUnsplit = (int)block_exclusive_scan(scanA, nList, warpSums);
+        const int newSize = C + nUnsplit;
+        if (newSize > M) { if (tid == 0) *A.errFlag = CSLAM_E_CAPACITY; break; }
+        if (tid == 0) sh_nToExpand = 0;
+        __syncthreads();
+        int myExp = 0;
+        for (int i = tid; i < nList; i += T) {
+            const QNode nd = cur[i];
+            if (splitF[i]) {
+                const int midX = nd.ulx + ((nd.brx - nd.ulx + 1) >> 1), midY = nd.uly + ((nd.bry - nd.uly + 1) >> 1);
+                int r = (int)scanB[ordOf[i]];
+                for (int q = 0; q < 4; q++) {
+                    const uint32_t c = childCnt[4 * i + q];
+                    if (c == 0) continue;
+                    QNode ch;
+                    ch.ulx = (q & 1) ? midX : nd.ulx; ch.brx = (q & 1) ? nd.brx : midX;
+                    ch.uly = (q & 2) ? midY : nd.uly; ch.bry = (q & 2) ? nd.bry : midY;
+                    ch.cnt = c; ch.flagE = c > 1; ch.seq = seqNext + r;
+                    const int pos = C - 1 - r;
+                    nxt[pos] = ch;
+                    childCnt[4 * i + q] = (uint32_t)pos;
+                    myExp += c > 1;
+                    r++;
+                }
+            } else {
+                const int pos = C + (int)scanA[i];
+                QNode keep = nd; keep.flagE = 0;
+                nxt[pos] = keep;
+                remap[i] = (uint16_t)pos;
+            }
+        }
+        if (myExp) atomicAdd(&sh_nToExpand, myExp);
+        __syncthreads();
+        for (int p = tid; p < n; p += T) {
+            const int i = pnode[p];
+            if (splitF[i]) {
+                const QNode nd = cur[i];
+                const uint32_t v = pts[p];
+                const int x = v & 0xfff, y = (v >> 12) & 0xfff;
+                const int midX = nd.ulx + ((nd.brx - nd.ulx + 1) >> 1), midY = nd.uly + ((nd.bry - nd.uly + 1) >> 1);
+                pnode[p] = (uint16_t)childCnt[4 * i + (x < midX ? 0 : 1) + (y < midY ? 0 : 2)];
+            } else {
+                pnode[p] = remap[i];
+            }
+        }
+        __syncthreads();
+        const int nToExpand = sh_nToExpand;
+        { QNode* t = cur; cur = nxt; nxt = t; }
+        nList = newSize; seqNext += C;
+        if (!finishMode) {
+            if (nList >= N || (nList == prevSize && nList >= N / 100)) break;
+            if (nList + 3 * nToExpand > N) finishMode = true;
+        } else {
+            if (nList >= N || nList == prevSize) break;
+        }
+        __syncthreads();
+    }
+    __syncthreads();
+    // ---- best key per node: max response, ties -> earliest in (cell row, cell col, y, x) order
+    // `best` aliases the inactive list buffer (M*8 bytes <= M*16).
+    unsigned long long* best = reinterpret_cast<unsigned long long*>(nxt);
+    for (int i = tid; i < nList; i += T) best[i] = 0ull;
+    __syncthreads();
+    for (int p = tid; p < n; p += T) {
+        const uint32_t v = pts[p];
+        const uint32_t x = v & 0xfff, y = (v >> 12) & 0xfff, r = v >> 24;
+        const uint32_t cy = (y - 3) / g.hCell, cx = (x - 3) / g.wCell;
+        const unsigned long long key = ((unsigned long long)cy << 32) | ((unsigned long long)cx << 24) | ((unsigned long long)y << 12) | x;
+        const unsigned long long packed = ((unsigned long long)(r + 1) << 40) | (0xffffffffffull - key);
+        atomicMax(&best[pnode[p]], packed);
+    }
+    __syncthreads();
+    // ---- cull (src/ORBExtractor.cpp:883-904) in list order, ordered compaction
+    for (int base = 0; base < nList; base += T) {
+        const int i = base + tid;
+        bool keep = false; uint32_t packedOut = 0;
+        if (i < nList) {
+            const unsigned long long b = best[i];
+            const uint32_t key = (uint32_t)(0xffffffffffull - (b & 0xffffffffffull));
+            const uint32_t x = key & 0xfff, y = (key >> 12) & 0xfff, r = (uint32_t)(b >> 40) - 1;
+            const uint32_t lx = x + g.minB, ly = y + g.minB;
+            const float ptx = __fmul_rn((float)lx, g.scale), pty = __fmul_rn((float)ly, g.scale);
+            const float fi = __fdiv_rn(ptx, (float)A.faceW), fj = __fdiv_rn(pty, (float)A.faceH);
+            const bool face = (fi >= 0 && fi < 1 && fj >= 1 && fj < 2) || (fi >= 1 && fi < 2 && fj >= 0 && fj < 3) || (fi >= 2 && fi < 3 && fj >= 1 && fj < 2);
+            const int mxI = (int)__fadd_rn(ptx, 0.5f), myI = (int)__fadd_rn(pty, 0.5f);
+            keep = face && !(ptx < 0 || mxI >= A.imgW || pty < 0 || myI >= A.imgH);
+            if (keep) keep = A.mask[(size_t)myI * A.maskPitch + mxI] != 0;
+            packedOut = lx | (ly << 12) | (r << 24);
+        }
+        scanA[tid] = keep ? 1u : 0u;
+        __syncthreads();
+        const uint32_t tot = block_exclusive_scan(scanA, T, warpSums);
+        if (tid == 0 && base == 0) sh_base = 0;
+        __syncthreads();
+        if (keep) {
+            const uint32_t pos = sh_base + scanA[tid];
+            if (pos < (uint32_t)A.keptCap) keptOut[pos] = packedOut; else *A.errFlag = CSLAM_E_CAPACITY;
+        }
+        __syncthreads();
+        if (tid == 0) sh_base += tot;
+        __syncthreads();
+        if (base + T >= nList && tid == 0) *keptCnt = min(sh_base, (uint32_t)A.keptCap);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------- k_describe
+struct DescribeArgs {
+    DevLevels L;
+    const uint32_t* kept; const uint32_t* keptCount; int keptCap;
+    cslam_keypoint* kps; uint8_t* desc; int32_t* nOut; int kpCap;
+    int* errFlag;
+};
+
+__global__ void __launch_bounds__(DESC_WARPS * 32) k_describe(DescribeArgs A) {
+    __shared__ uint8_t s_patch[DESC_WARPS][43 * 44];
+    __shared__ uint16_t s_h[DESC_WARPS][43 * 38];
+    __shared__ uint8_t s_blur[DESC_WARPS][37 * 40];
+    __shared__ signed char s_pat[1024];
+    const int level = blockIdx.y, frame = blockIdx.z;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int i = threadIdx.x; i < 1024; i += blockDim.x) s_pat[i] = c_pattern[i];
+    __syncthreads();
+    const uint32_t* kc = A.keptCount + (size_t)frame * A.L.nlevels;
+    const int slot = blockIdx.x * DESC_WARPS + warp;
+    int offset = 0, total = 0;
+    for (int l = 0; l < A.L.nlevels; l++) { const int c = (int)kc[l]; if (l < level) offset += c; total += c; }
+    if (blockIdx.x == 0 && level == 0 && threadIdx.x == 0) A.nOut[frame] = min(total, A.kpCap);
+    if (slot >= (int)kc[level]) return;
+    const int outIdx = offset + slot;
+    if (outIdx >= A.kpCap) { if (lane == 0) *A.errFlag = CSLAM_E_CAPACITY; return; }
+    const LevelGeom g = A.L.g[level];
+    const uint8_t* I = A.L.img[level] + (size_t)frame * g.pitch * g.h;
+    const uint32_t v = A.kept[((size_t)frame * A.L.nlevels + level) * A.keptCap + slot];
+    const int kx = v & 0xfff, ky = (v >> 12) & 0xfff, resp = v >> 24;
+
+    // ---- 43x43 neighbourhood (REFLECT_101 at the level edges, like the blur of the apron-less clone)
+    uint8_t* P = s_patch[warp];
+    for (int i = lane; i < 43 * 43; i += 32) {
+        const int r = i / 43, c = i - r * 43;
+        const int yy = reflect101(ky - 21 + r, g.h), xx = reflect101(kx - 21 + c, g.w);
+        P[r * 44 + c] = __ldg(I + (size_t)yy * g.pitch + xx);
+    }
+    __syncwarp();
+    // ---- IC_Angle on the unblurred patch: lane = column u in [-15,15]
+    int m10 = 0, m01 = 0;
+    if (lane < 31) {
+        const int u = lane - HALF_PATCH;
+        int colsum = 0;
+        for (int vv = -HALF_PATCH; vv <= HALF_PATCH; vv++) {
+            const int av = vv < 0 ? -vv : vv;
+            if ((u < 0 ? -u : u) <= c_umax[av]) {
+                const int val = P[(21 + vv) * 44 + 21 + u];
+                colsum += val; m01 += vv * val;
+            }
+        }
+        m10 = u * colsum;
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) { m10 += __shfl_xor_sync(0xffffffffu, m10, o); m01 += __shfl_xor_sync(0xffffffffu, m01, o); }
+    const float angle = fast_atan2_deg((float)m01, (float)m10);
+    // ---- 7x7 sigma-2 Gaussian, OpenCV 8.8 fixed point [18,34,48,56,48,34,18], only where BRIEF can sample (+-18)
+    uint16_t* Hh = s_h[warp];
+    for (int i = lane; i < 43 * 37; i += 32) {
+        const int r = i / 37, c = i - r * 37;
+        const uint8_t* q = P + r * 44 + c;
+        Hh[r * 38 + c] = (uint16_t)(18 * (q[0] + q[6]) + 34 * (q[1] + q[5]) + 48 * (q[2] + q[4]) + 56 * q[3]);
+    }
+    __syncwarp();
+    uint8_t* Bl = s_blur[warp];
+    for (int i = lane; i < 37 * 37; i += 32) {
+        const int r = i / 37, c = i - r * 37;
+        const uint16_t* q = Hh + r * 38 + c;
+        const uint32_t s = 18u * (q[0] + q[6 * 38]) + 34u * (q[38] + q[5 * 38]) + 48u * (q[2 * 38] + q[4 * 38]) + 56u * q[3 * 38];
+        Bl[r * 40 + c] = (uint8_t)((s + 32768u) >> 16);
+    }
+    __syncwarp();
+    // ---- steered BRIEF: lane = output byte
+    const float factorPI = (float)(3.14159265358979323846 / 180.0);
+    float a, b;
+    det_sincosf(__fmul_rn(angle, factorPI), &b, &a);
+    const signed char* pat = s_pat + lane * 32;
+    uint32_t val = 0;
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+        const float x0 = (float)pat[4 * k], y0 = (float)pat[4 * k + 1], x1 = (float)pat[4 * k + 2], y1 = (float)pat[4 * k + 3];
+        const int r0 = __float2int_rn(__fadd_rn(__fmul_rn(x0, b), __fmul_rn(y0, a))), c0 = __float2int_rn(__fsub_rn(__fmul_rn(x0, a), __fmul_rn(y0, b)));
+        const int r1 = __float2int_rn(__fadd_rn(__fmul_rn(x1, b), __fmul_rn(y1, a))), c1 = __float2int_rn(__fsub_rn(__fmul_rn(x1, a), __fmul_rn(y1, b)));
+        const int t0 = Bl[(r0 + 18) * 40 + c0 + 18], t1 = Bl[(r1 + 18) * 40 + c1 + 18];
+        val |= (uint32_t)(t0 < t1) << k;
+    }
+    A.desc[((size_t)frame * A.kpCap + outIdx) * 32 + lane] = (uint8_t)val;
+    if (lane == 0) {
+        cslam_keypoint kp;
+        kp.x = __fmul_rn((float)kx, g.scale); kp.y = __fmul_rn((float)ky, g.scale);
+        kp.size = g.sizeF; kp.angle = angle; kp.response = (float)resp; kp.octave = level; kp.class_id = -1;
+        A.kps[(size_t)frame * A.kpCap + outIdx] = kp;
+    }
+}
+
+}  // namespace cslam
+
+// =================================================================================================== host side
+using namespace cslam;
+
+struct cslam_frontend {
+    int device = 0;
+    cslam_cam_params cam;
+    cslam_orb_params orb;
+    int W = 0, H = 0, CW = 0, CH = 0, maxBatch = 0, kpCap = 0, keptCap = 0, M = 0;
+    cudaStream_t stream = nullptr;
+    DevLevels L;                     // host copy of the device-pointer table (passed by value to kernels)
+    std::vector<float> scale, invScale, sigma2, invSigma2; std::vector<int> perLevel; int umax[16];
+    std::vector<float> map1, map2;   // host float maps (3H x 3W), kept for cslam_frontend_get_maps
+    uint32_t* d_map = nullptr;       // 5 x W x W
+    uint8_t* d_mask = nullptr; int maskPitch = 0;
+    uint8_t* d_fisheye = nullptr;    // staging for host entry points: maxBatch x Ih x Iw
+    uint32_t* d_candCount = nullptr; // maxBatch x nlevels
+    uint32_t* d_kept = nullptr; uint32_t* d_keptCount = nullptr;
+    cslam_keypoint* d_kps = nullptr; uint8_t* d_desc = nullptr; int32_t* d_nout = nullptr;
+    int* d_err = nullptr;
+    uint8_t* h_pin_in = nullptr; cslam_keypoint* h_pin_kps = nullptr; uint8_t* h_pin_desc = nullptr; int32_t* h_pin_n = nullptr; int* h_pin_err = nullptr;
+    std::vector<void*> owned;
+    int64_t launches = 0;
+    int lastBatch = 0;
+    bool cornersDirty = false;   // level-0 buffer holds caller canvases (non-zero corner tiles) from cslam_orb_extract
+    size_t distributeSmem = 0;
+};
+
+static inline int cv_round_f(float v) { return (int)lrintf(v); }
+static inline int cv_round_d(double v) { return (int)lrint(v); }
+
+// CamModelGeneral::CubemapToFisheye (src/CamModelGeneral.cpp:265-290) + WorldToImg (include/CamModelGeneral.h:359-374):
+// start-up code on the host, exactly where the reference runs it (System::CreateUndistortRectifyMap).
+static void host_cubemap_to_fisheye(const cslam_cam_params& cp, double up, double vp, double& uf, double& vf) {
+    float i = (float)up, j = (float)vp;
+    uf = -1; vf = -1;
+    const float fi = i / (float)cp.face_w, fj = j / (float)cp.face_h;
+    int face = -1;   // 0 front 1 left 2 right 3 upper 4 lower
+    if (fi >= 0 && fi < 1 && fj >= 1 && fj < 2) face = 1;
+    else if (fi >= 1 && fi < 2 && fj >= 0 && fj < 1) face = 3;
+    else if (fi >= 1 && fi < 2 && fj >= 1 && fj < 2) face = 0;
+    else if (fi >= 1 && fi < 2 && fj >= 2 && fj < 3) face = 4;
+    else if (fi >= 2 && fi < 3 && fj >= 1 && fj < 2) face = 2;
+    if (face < 0) return;
+    const double fx = cp.face_w / 2.0, fy = cp.face_h / 2.0;
+    i = i - static_cast<int>(i / cp.face_w) * cp.face_w;
+    j = j - static_cast<int>(j / cp.face_h) * cp.face_h;
+    const double lz = 1.0, lx = (i - fx) * lz / fx, ly = (j - fy) * lz / fy;
+    double X, Y, Z;
+    switch (face) {
+        case 0: X = lx; Y = ly; Z = lz; break;
+        case 1: X = -lz; Y = ly; Z = lx; break;
+        case 2: X = lz; Y = ly; Z = -lx; break;
+        case 4: X = lx; Y = lz; Z = -ly; break;
+        default: X = lx; Y = -lz; Z = ly; break;
+    }
+    double norm = std::sqrt(X * X + Y * Y);
+    if (norm == 0.0) norm = 1e-14;
+    const double theta = std::atan(-Z / norm);
+    double rho = 0.0;
+    for (int k = 11; k >= 0; k--) rho = rho * theta + cp.invpoly[k];
+    const double uu = X / norm * rho, vv = Y / norm * rho;
+    uf = uu * cp.c + vv * cp.d + cp.u0;
+    vf = uu * cp.e + vv + cp.v0;
+    if (uf < 0 || uf >= cp.Iw || vf < 0 || vf >= cp.Ih) { uf = -1; vf = -1; }
+}
+
+template <class T>
+static int dev_alloc(cslam_frontend* fe, T** p, size_t count, bool zero = true) {
+    void* q = nullptr;
+    CSLAM_CUDA(cudaMalloc(&q, count * sizeof(T)));
+    if (zero) CSLAM_CUDA(cudaMemset(q, 0, count * sizeof(T)));
+    fe->owned.push_back(q);
+    *p = (T*)q;
+    return 0;
+}
+template <class T>
+static int dev_upload(cslam_frontend* fe, const T** p, const std::vector<T>& v) {
+    T* q = nullptr;
+    int rc = dev_alloc(fe, &q, v.size(), false);
+    if (rc) return rc;
+    CSLAM_CUDA(cudaMemcpy(q, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice));
+    *p = q;
+    return 0;
+}
+
+static void build_resize_tables(int sn, int dn, std::vector<uint16_t>& ofs, std::vector<uint32_t>& ab) {
+    ofs.resize(dn); ab.resize(dn);
+    const double scale = (double)sn / dn;
+    for (int d = 0; d < dn; d++) {
+        float f = (float)((d + 0.5) * scale - 0.5);
+        int s = (int)std::floor(f);
+        f -= s;
+        if (s < 0) { s = 0; f = 0; }
+        if (s >= sn - 1) { s = sn - 1; f = 0; }
+        const int a0 = cv_round_f((1.f - f) * 2048.f), a1 = cv_round_f(f * 2048.f);
+        ofs[d] = (uint16_t)s; ab[d] = (uint32_t)a0 | ((uint32_t)a1 << 16);
+    }
+}
+
+extern "C" int cslam_frontend_create(cslam_frontend** out, int device, const cslam_cam_params* cam, const cslam_orb_params* orb,
+                                     const uint8_t* mask, int mask_pitch, int max_batch) {
+    if (!out || !cam || !orb || !mask || max_batch <= 0) { set_error("cslam_frontend_create: null/invalid argument"); return CSLAM_E_BADARG; }
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) { set_error("no CUDA device (this library has no CPU fallback)"); return CSLAM_E_NODEVICE; }
+    if (device < 0 || device >= ndev) { set_error("device %d out of range (%d devices)", device, ndev); return CSLAM_E_BADARG; }
+    if (cam->face_w != cam->face_h || cam->face_w <= 0) { set_error("cube faces must be square (got %dx%d)", cam->face_w, cam->face_h); return CSLAM_E_BADARG; }
+    if (3 * cam->face_w > 4095 || cam->Iw * 32 > 65535 || cam->Ih * 32 > 65535) { set_error("image too large for the packed coordinate formats"); return CSLAM_E_BADARG; }
+    if (orb->nlevels < 1 || orb->nlevels > MAX_LEVELS || orb->nfeatures < 1 || orb->scale_factor <= 1.f) { set_error("bad ORB parameters"); return CSLAM_E_BADARG; }
+    CSLAM_CUDA(cudaSetDevice(device));
+    cslam_frontend* fe = new cslam_frontend;
+    fe->device = device; fe->cam = *cam; fe->orb = *orb; fe->maxBatch = max_batch;
+    fe->W = cam->face_w; fe->H = cam->face_h; fe->CW = 3 * fe->W; fe->CH = 3 * fe->H;
+    const int nl = orb->nlevels;
+    // ---- ORBextractor::ORBextractor (src/ORBExtractor.cpp:381-442): scale tables, per-level quotas, umax
+    fe->scale.resize(nl); fe->invScale.resize(nl); fe->sigma2.resize(nl); fe->invSigma2.resize(nl); fe->perLevel.resize(nl);
+    fe->scale[0] = 1.f; fe->sigma2[0] = 1.f;
+    for (int i = 1; i < nl; i++) { fe->scale[i] = fe->scale[i - 1] * orb->scale_factor; fe->sigma2[i] = fe->scale[i] * fe->scale[i]; }
+    for (int i = 0; i < nl; i++) { fe->invScale[i] = 1.0f / fe->scale[i]; fe->invSigma2[i] = 1.0f / fe->sigma2[i]; }
+    {
+        const float factor = 1.0f / orb->scale_factor;
+        float nDesired = orb->nfeatures * (1 - factor) / (1 - (float)std::pow((double)factor, (double)nl));
+        int sum = 0;
+        for (int l = 0; l < nl - 1; l++) { fe->perLevel[l] = cv_round_f(nDesired); sum += fe->perLevel[l]; nDesired *= factor; }
+        fe->perLevel[nl - 1] = std::max(orb->nfeatures - sum, 0);
+        int v, v0, vmax = (int)std::floor(HALF_PATCH * std::sqrt(2.f) / 2 + 1), vmin = (int)std::ceil(HALF_PATCH * std::sqrt(2.f) / 2);
+        const double hp2 = HALF_PATCH * HALF_PATCH;
+        for (v = 0; v <= vmax; ++v) fe->umax[v] = cv_round_d(std::sqrt(hp2 - v * v));
+        for (v = HALF_PATCH, v0 = 0; v >= vmin; --v) { while (fe->umax[v0] == fe->umax[v0 + 1]) ++v0; fe->umax[v] = v0; ++v0; }
+    }
+    int rc = 0;
+    auto fail = [&](int code) { cslam_frontend_destroy(fe); return code; };
+    if (cudaStreamCreateWithFlags(&fe->stream, cudaStreamNonBlocking) != cudaSuccess) { set_error("cudaStreamCreate failed"); return fail(CSLAM_E_CUDA); }
+    if (cudaMemcpyToSymbol(c_umax, fe->umax, sizeof(fe->umax)) != cudaSuccess) { set_error("cudaMemcpyToSymbol failed"); return fail(CSLAM_E_CUDA); }
+    // ---- level geometry (ComputePyramid :930-936, ComputeKeyPointsOctTree :747-761)
+    std::memset(&fe->L, 0, sizeof(fe->L));
+    fe->L.nlevels = nl;
+    int maxQuota = 0;
+    for (int l = 0; l < nl; l++) {
+        LevelGeom& g = fe->L.g[l];
+        g.w = cv_round_f((float)fe->CW * fe->invScale[l]); g.h = cv_round_f((float)fe->CH * fe->invScale[l]);
+        g.pitch = round_up(g.w, 128);
+        g.minB = EDGE_THRESHOLD - 3; g.maxBX = g.w - EDGE_THRESHOLD + 3; g.maxBY = g.h - EDGE_THRESHOLD + 3;
+        const float width = (float)(g.maxBX - g.minB), height = (float)(g.maxBY - g.minB);
+        const int nCols = (int)(width / 30.f), nRows = (int)(height / 30.f);
+        if (nCols < 1 || nRows < 1) { set_error("pyramid level %d (%dx%d) is too small for the 30-px FAST grid", l, g.w, g.h); return fail(CSLAM_E_BADARG); }
+        g.wCell = (int)std::ceil(width / nCols); g.hCell = (int)std::ceil(height / nRows);
+        if (g.wCell > CELL_MAX || g.hCell > CELL_MAX) { set_error("FAST cell %dx%d exceeds the supported %d px", g.wCell, g.hCell, CELL_MAX); return fail(CSLAM_E_BADARG); }
+        g.nColsEff = 0; g.nRowsEff = 0;
+        for (int j = 0; j < nCols; j++) if (!((float)(g.minB + j * g.wCell) >= g.maxBX - 6)) g.nColsEff = j + 1;
+        for (int i = 0; i < nRows; i++) if (!((float)(g.minB + i * g.hCell) >= g.maxBY - 3)) g.nRowsEff = i + 1;
+        g.quota = fe->perLevel[l]; maxQuota = std::max(maxQuota, g.quota);
+        g.candCap = std::max(4096, g.nColsEff * g.nRowsEff * 32);
+        g.scale = fe->scale[l]; g.sizeF = (float)(int)(PATCH_SIZE * fe->scale[l]);
+        if ((rc = dev_alloc(fe, &fe->L.img[l], (size_t)max_batch * g.pitch * g.h))) return fail(rc);
+        if ((rc = dev_alloc(fe, &fe->L.cand[l], (size_t)max_batch * g.candCap, false))) return fail(rc);
+        if ((rc = dev_alloc(fe, &fe->L.pnode[l], (size_t)max_batch * g.candCap, false))) return fail(rc);
+        if (l > 0) {
+            std::vector<uint16_t> xo, yo; std::vector<uint32_t> xa, ya;
+            build_resize_tables(fe->L.g[l - 1].w, g.w, xo, xa); build_resize_tables(fe->L.g[l - 1].h, g.h, yo, ya);
+            if ((rc = dev_upload(fe, &fe->L.xofs[l], xo)) || (rc = dev_upload(fe, &fe->L.xab[l], xa)) || (rc = dev_upload(fe, &fe->L.yofs[l], yo)) ||
+                (rc = dev_upload(fe, &fe->L.yab[l], ya))) return fail(rc);
+        }
+    }
+    fe->M = round_up(std::max(maxQuota + 4, 16), 32);
+    fe->keptCap = fe->M;
+    fe->kpCap = orb->nfeatures + 3 * nl;
+    fe->distributeSmem = (size_t)fe->M * (2 * sizeof(QNode) + 4 * 4 + 4 + 4 + 2 + 2 + 1);
+    fe->distributeSmem = (fe->distributeSmem + 15) & ~(size_t)15;
+    if (fe->distributeSmem > 200 * 1024) { set_error("nfeatures too large for the shared-memory quadtree (%zu B)", fe->distributeSmem); return fail(CSLAM_E_BADARG); }
+    if (cudaFuncSetAttribute(k_distribute, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fe->distributeSmem) != cudaSuccess) { set_error("cudaFuncSetAttribute failed"); return fail(CSLAM_E_CUDA); }
+    // ---- System::CreateUndistortRectifyMap (src/System.cpp:301-324) on the host, then quantised like cv::remap does
+    {
+        const int CW = fe->CW, CH = fe->CH, W = fe->W;
+        fe->map1.assign((size_t)CW * CH, 0.f); fe->map2.assign((size_t)CW * CH, 0.f);
+        for (int y = 0; y < CH; y++)
+            for (int x = 0; x < CW; x++) {
+                double u, v;
+                host_cubemap_to_fisheye(*cam, (double)x, (double)y, u, v);
+                if (u < 0 || v < 0 || u >= cam->Iw || v >= cam->Ih) continue;
+                fe->map1[(size_t)y * CW + x] = (float)u; fe->map2[(size_t)y * CW + x] = (float)v;
+            }
+        std::vector<uint32_t> q((size_t)5 * W * W);
+        const int tc[5] = {1, 0, 2, 1, 1}, tr[5] = {1, 1, 1, 0, 2};
+        for (int f = 0; f < 5; f++)
+            for (int y = 0; y < W; y++)
+                for (int x = 0; x < W; x++) {
+                    const size_t src = (size_t)(tr[f] * W + y) * CW + tc[f] * W + x;
+                    const int sx = cv_round_f(fe->map1[src] * 32.f), sy = cv_round_f(fe->map2[src] * 32.f);
+                    q[((size_t)f * W + y) * W + x] = (uint32_t)sx | ((uint32_t)sy << 16);
+                }
+        const uint32_t* dq = nullptr;
+        if ((rc = dev_upload(fe, &dq, q))) return fail(rc);
+        fe->d_map = const_cast<uint32_t*>(dq);
+    }
+    // ---- mask
+    fe->maskPitch = round_up(fe->CW, 128);
+    if ((rc = dev_alloc(fe, &fe->d_mask, (size_t)fe->maskPitch * fe->CH))) return fail(rc);
+    if (cudaMemcpy2D(fe->d_mask, fe->maskPitch, mask, mask_pitch, fe->CW, fe->CH, cudaMemcpyHostToDevice) != cudaSuccess) { set_error("mask upload failed"); return fail(CSLAM_E_CUDA); }
+    // ---- batch buffers
+    const size_t B = max_batch;
+    if ((rc = dev_alloc(fe, &fe->d_fisheye, B * cam->Iw * cam->Ih)) || (rc = dev_alloc(fe, &fe->d_candCount, B * nl)) ||
+        (rc = dev_alloc(fe, &fe->d_kept, B * nl * fe->keptCap)) || (rc = dev_alloc(fe, &fe->d_keptCount, B * nl)) ||
+        (rc = dev_alloc(fe, &fe->d_kps, B * fe->kpCap)) || (rc = dev_alloc(fe, &fe->d_desc, B * fe->kpCap * 32)) ||
+        (rc = dev_alloc(fe, &fe->d_nout, B)) || (rc = dev_alloc(fe, &fe->d_err, 1))) return fail(rc);
+    const size_t inBytes = std::max((size_t)cam->Iw * cam->Ih, (size_t)fe->L.g[0].pitch * fe->CH) * B;
+    if (cudaMallocHost(&fe->h_pin_in, inBytes) != cudaSuccess || cudaMallocHost(&fe->h_pin_kps, B * fe->kpCap * sizeof(cslam_keypoint)) != cudaSuccess ||
+        cudaMallocHost(&fe->h_pin_desc, B * fe->kpCap * 32) != cudaSuccess || cudaMallocHost(&fe->h_pin_n, B * sizeof(int32_t)) != cudaSuccess ||
+        cudaMallocHost(&fe->h_pin_err, sizeof(int)) != cudaSuccess) { set_error("pinned host allocation failed"); return fail(CSLAM_E_CUDA); }
+    *out = fe;
+    return CSLAM_OK;
+}
+
+extern "C" void cslam_frontend_destroy(cslam_frontend* fe) {
+    if (!fe) return;
+    cudaSetDevice(fe->device);
+    if (fe->stream) { cudaStreamSynchronize(fe->stream); cudaStreamDestroy(fe->stream); }
+    for (void* p : fe->owned) cudaFree(p);
+    if (fe->h_pin_in) cudaFreeHost(fe->h_pin_in);
+    if (fe->h_pin_kps) cudaFreeHost(fe->h_pin_kps);
+    if (fe->h_pin_desc) cudaFreeHost(fe->h_pin_desc);
+    if (fe->h_pin_n) cudaFreeHost(fe->h_pin_n);
+    if (fe->h_pin_err) cudaFreeHost(fe->h_pin_err);
+    delete fe;
+}
+
+extern "C" int cslam_frontend_kp_capacity(const cslam_frontend* fe) { return fe ? fe->kpCap : 0; }
+extern "C" void* cslam_frontend_stream(const cslam_frontend* fe) { return fe ? (void*)fe->stream : nullptr; }
+extern "C" int64_t cslam_frontend_launches(const cslam_frontend* fe) { return fe ? fe->launches : 0; }
+
+extern "C" int cslam_frontend_sync(cslam_frontend* fe) {
+    if (!fe) return CSLAM_E_BADARG;
+    CSLAM_CUDA(cudaMemcpyAsync(fe->h_pin_err, fe->d_err, sizeof(int), cudaMemcpyDeviceToHost, fe->stream));
+    CSLAM_CUDA(cudaStreamSynchronize(fe->stream));
+    if (*fe->h_pin_err != 0) {
+        const int code = *fe->h_pin_err;
+        cudaMemsetAsync(fe->d_err, 0, sizeof(int), fe->stream);
+        set_error("front end: a fixed-capacity buffer overflowed on the device (candidates / nodes / keypoints)");
+        return code;
+    }
+    return CSLAM_OK;
+}
+
+static int launch_warp(cslam_frontend* fe, const uint8_t* d_fisheye, int batch) {
+    const int FPT = 4;
+    if (fe->cornersDirty) {   // the warp never writes the 4 corner tiles; they must read as the reference's zeroed canvas
+        CSLAM_CUDA(cudaMemsetAsync(fe->L.img[0], 0, (size_t)fe->maxBatch * fe->L.g[0].pitch * fe->CH, fe->stream));
+        fe->cornersDirty = false;
+    }
+    dim3 grid(cdiv(fe->W, 256), fe->H, 5 * cdiv(batch, FPT));
+    k_warp<FPT><<<grid, 256, 0, fe->stream>>>(d_fisheye, fe->cam.Iw, fe->cam.Ih, fe->d_map, fe->W, fe->L.img[0], fe->L.g[0].pitch,
+                                               (size_t)fe->L.g[0].pitch * fe->CH, batch);
+    fe->launches++;
+    CSLAM_CUDA(cudaGetLastError());
+    return 0;
+}
+
+static int launch_extract(cslam_frontend* fe, int batch, cslam_keypoint* d_kps, uint8_t* d_desc, int32_t* d_nout) {
+    const int nl = fe->L.nlevels;
+    fe->lastBatch = batch;
+    CSLAM_CUDA(cudaMemsetAsync(fe->d_candCount, 0, (size_t)batch * nl * sizeof(uint32_t), fe->stream));
+    for (int l = 1; l < nl; l++) {
+        const LevelGeom& s = fe->L.g[l - 1]; const LevelGeom& d = fe->L.g[l];
+        dim3 grid(cdiv(cdiv(d.w, 4), 256), d.h, batch);
+        k_pyramid<<<grid, 256, 0, fe->stream>>>(fe->L.img[l - 1], s.w, s.h, s.pitch, fe->L.img[l], d.w, d.h, d.pitch, fe->L.xofs[l], fe->L.xab[l], fe->L.yofs[l], fe->L.yab[l]);
+        fe->launches++;
+    }
+    for (int l = 0; l < nl; l++) {
+        const LevelGeom& g = fe->L.g[l];
+        dim3 grid(cdiv(g.nColsEff, CG), g.nRowsEff, batch);
+        k_fast<<<grid, 256, 0, fe->stream>>>(fe->L.img[l], g, fe->orb.ini_th_fast, fe->orb.min_th_fast, fe->L.cand[l], fe->d_candCount + l, nl, fe->d_err);
+        fe->launches++;
+    }
+    CSLAM_CUDA(cudaGetLastError());
+    DistributeArgs da;
+    da.L = fe->L; da.candCount = fe->d_candCount; da.kept = fe->d_kept; da.keptCount = fe->d_keptCount; da.mask = fe->d_mask; da.maskPitch = fe->maskPitch;
+    da.imgW = fe->CW; da.imgH = fe->CH; da.faceW = fe->W; da.faceH = fe->H; da.keptCap = fe->keptCap; da.M = fe->M; da.errFlag = fe->d_err;
+    k_distribute<<<dim3(nl, batch), 256, fe->distributeSmem, fe->stream>>>(da);
+    fe->launches++;
+    DescribeArgs ds;
+    ds.L = fe->L; ds.kept = fe->d_kept; ds.keptCount = fe->d_keptCount; ds.keptCap = fe->keptCap; ds.kps = d_kps; ds.desc = d_desc; ds.nOut = d_nout; ds.kpCap = fe->kpCap;
+    ds.errFlag = fe->d_err;
+    k_describe<<<dim3(cdiv(fe->keptCap, DESC_WARPS), nl, batch), DESC_WARPS * 32, 0, fe->stream>>>(ds);
+    fe->launches++;
+    CSLAM_CUDA(cudaGetLastError());
+    return 0;
+}
+
+static int check_batch(cslam_frontend* fe, int batch, const void* a, const void* b) {
+    if (!fe || !a || !b || batch <= 0 || batch > fe->maxBatch) { set_error("bad argument (batch must be in 1..%d)", fe ? fe->maxBatch : 0); return CSLAM_E_BADARG; }
+    CSLAM_CUDA(cudaSetDevice(fe->device));
+    return 0;
+}
+
+extern "C" int cslam_warp(cslam_frontend* fe, const uint8_t* fisheye, int batch, uint8_t* canvas, int canvas_pitch) {
+    int rc = check_batch(fe, batch, fisheye, canvas);
+    if (rc) return rc;
+    const size_t fb = (size_t)fe->cam.Iw * fe->cam.Ih * batch;
+    std::memcpy(fe->h_pin_in, fisheye, fb);
+    CSLAM_CUDA(cudaMemcpyAsync(fe->d_fisheye, fe->h_pin_in, fb, cudaMemcpyHostToDevice, fe->stream));
+    if ((rc = launch_warp(fe, fe->d_fisheye, batch))) return rc;
+    // the reference writes only the five face ROIs; corner tiles of the caller's canvas are left untouched
+    const int W = fe->W, pitch = fe->L.g[0].pitch;
+    const int tc[5] = {1, 0, 2, 1, 1}, tr[5] = {1, 1, 1, 0, 2};
+    for (int f = 0; f < batch; f++)
+        for (int t = 0; t < 5; t++)
+            CSLAM_CUDA(cudaMemcpy2DAsync(canvas + (size_t)f * canvas_pitch * fe->CH + (size_t)tr[t] * W * canvas_pitch + tc[t] * W, canvas_pitch,
+                                         fe->L.img[0] + (size_t)f * pitch * fe->CH + (size_t)tr[t] * W * pitch + tc[t] * W, pitch, W, W, cudaMemcpyDeviceToHost, fe->stream));
+    return cslam_frontend_sync(fe);
+}
+
+static int download_results(cslam_frontend* fe, int batch, cslam_keypoint* kps, uint8_t* desc, int32_t* n_out) {
+    const size_t nk = (size_t)batch * fe->kpCap;
+    CSLAM_CUDA(cudaMemcpyAsync(fe->h_pin_kps, fe->d_kps, nk * sizeof(cslam_keypoint), cudaMemcpyDeviceToHost, fe->stream));
+    CSLAM_CUDA(cudaMemcpyAsync(fe->h_pin_desc, fe->d_desc, nk * 32, cudaMemcpyDeviceToHost, fe->stream));
+    CSLAM_CUDA(cudaMemcpyAsync(fe->h_pin_n, fe->d_nout, batch * sizeof(int32_t), cudaMemcpyDeviceToHost, fe->stream));
+    int rc = cslam_frontend_sync(fe);
+    if (rc) return rc;
+    std::memcpy(kps, fe->h_pin_kps, nk * sizeof(cslam_keypoint));
+    std::memcpy(desc, fe->h_pin_desc, nk * 32);
+    std::memcpy(n_out, fe->h_pin_n, batch * sizeof(int32_t));
+    return CSLAM_OK;
+}
+
+extern "C" int cslam_orb_extract(cslam_frontend* fe, const uint8_t* canvas, int canvas_pitch, int batch, cslam_keypoint* kps, uint8_t* desc, int32_t* n_out) {
+    int rc = check_batch(fe, batch, canvas, kps);
+    if (rc) return rc;
+    if (!desc || !n_out || canvas_pitch < fe->CW) { set_error("cslam_orb_extract: bad argument"); return CSLAM_E_BADARG; }
+    const int pitch = fe->L.g[0].pitch;
+    CSLAM_CUDA(cudaMemcpy2DAsync(fe->L.img[0], pitch, canvas, canvas_pitch, fe->CW, (size_t)fe->CH * batch, cudaMemcpyHostToDevice, fe->stream));
+    fe->cornersDirty = true;
+    if ((rc = launch_extract(fe, batch, fe->d_kps, fe->d_desc, fe->d_nout))) return rc;
+    return download_results(fe, batch, kps, desc, n_out);
+}
+
+extern "C" int cslam_frontend_run(cslam_frontend* fe, const uint8_t* fisheye, int batch, cslam_keypoint* kps, uint8_t* desc, int32_t* n_out) {
+    int rc = check_batch(fe, batch, fisheye, kps);
+    if (rc) return rc;
+    if (!desc || !n_out) { set_error("cslam_frontend_run: null output"); return CSLAM_E_BADARG; }
+    const size_t fb = (size_t)fe->cam.Iw * fe->cam.Ih * batch;
+    std::memcpy(fe->h_pin_in, fisheye, fb);
+    CSLAM_CUDA(cudaMemcpyAsync(fe->d_fisheye, fe->h_pin_in, fb, cudaMemcpyHostToDevice, fe->stream));
+    if ((rc = launch_warp(fe, fe->d_fisheye, batch))) return rc;
+    if ((rc = launch_extract(fe, batch, fe->d_kps, fe->d_desc, fe->d_nout))) return rc;
+    return download_results(fe, batch, kps, desc, n_out);
+}
+
+extern "C" int cslam_frontend_run_dev(cslam_frontend* fe, const uint8_t* fisheye_dev, int batch, cslam_keypoint* kps_dev, uint8_t* desc_dev, int32_t* n_out_dev) {
+    int rc = check_batch(fe, batch, fisheye_dev, kps_dev);
+    if (rc) return rc;
+    if (!desc_dev || !n_out_dev) { set_error("cslam_frontend_run_dev: null output"); return CSLAM_E_BADARG; }
+    if ((rc = launch_warp(fe, fisheye_dev, batch))) return rc;
+    return launch_extract(fe, batch, kps_dev, desc_dev, n_out_dev);
+}
+
+extern "C" int cslam_frontend_level_size(const cslam_frontend* fe, int level, int* w, int* h) {
+    if (!fe || level < 0 || level >= fe->L.nlevels) return CSLAM_E_BADARG;
+    *w = fe->L.g[level].w; *h = fe->L.g[level].h;
+    return CSLAM_OK;
+}
+extern "C" int cslam_frontend_get_level(cslam_frontend* fe, int frame, int level, uint8_t* out) {
+    if (!fe || level < 0 || level >= fe->L.nlevels || frame < 0 || frame >= fe->maxBatch || !out) return CSLAM_E_BADARG;
+    const LevelGeom& g = fe->L.g[level];
+    CSLAM_CUDA(cudaSetDevice(fe->device));
+    CSLAM_CUDA(cudaStreamSynchronize(fe->stream));
+    CSLAM_CUDA(cudaMemcpy2D(out, g.w, fe->L.img[level] + (size_t)frame * g.pitch * g.h, g.pitch, g.w, g.h, cudaMemcpyDeviceToHost));
+    return CSLAM_OK;
+}
+extern "C" int cslam_frontend_get_candidates(cslam_frontend* fe, int frame, int level, int32_t* xyr, int cap, int* n) {
+    if (!fe || level < 0 || level >= fe->L.nlevels || frame < 0 || frame >= fe->maxBatch || !xyr || !n) return CSLAM_E_BADARG;
+    const LevelGeom& g = fe->L.g[level];
+    CSLAM_CUDA(cudaSetDevice(fe->device));
+    CSLAM_CUDA(cudaStreamSynchronize(fe->stream));
+    uint32_t cnt = 0;
+    CSLAM_CUDA(cudaMemcpy(&cnt, fe->d_candCount + (size_t)frame * fe->L.nlevels + level, 4, cudaMemcpyDeviceToHost));
+    const int m = (int)std::min<uint32_t>(cnt, (uint32_t)g.candCap);
+    std::vector<uint32_t> tmp(m);
+    if (m) CSLAM_CUDA(cudaMemcpy(tmp.data(), fe->L.cand[level] + (size_t)frame * g.candCap, (size_t)m * 4, cudaMemcpyDeviceToHost));
+    for (int i = 0; i < m && i < cap; i++) { xyr[3 * i] = tmp[i] & 0xfff; xyr[3 * i + 1] = (tmp[i] >> 12) & 0xfff; xyr[3 * i + 2] = tmp[i] >> 24; }
+    *n = m;
+    return CSLAM_OK;
+}
+extern "C" int cslam_frontend_get_maps(const cslam_frontend* fe, float* map1, float* map2) {
+    if (!fe || !map1 || !map2) return CSLAM_E_BADARG;
+    std::memcpy(map1, fe->map1.data(), fe->map1.size() * 4); std::memcpy(map2, fe->map2.data(), fe->map2.size() * 4);
+    return CSLAM_OK;
+}
+extern "C" int cslam_frontend_tables(const cslam_frontend* fe, float* scale, float* inv_scale, float* sigma2, float* inv_sigma2, int32_t* per, int32_t* umax16) {
+    if (!fe) return CSLAM_E_BADARG;
+    for (int i = 0; i < fe->L.nlevels; i++) { scale[i] = fe->scale[i]; inv_scale[i] = fe->invScale[i]; sigma2[i] = fe->sigma2[i]; inv_sigma2[i] = fe->invSigma2[i]; per[i] = fe->perLevel[i]; }
+    for (int i = 0; i < 16; i++) umax16[i] = fe->umax[i];
+    return CSLAM_OK;
+}

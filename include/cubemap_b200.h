@@ -1,0 +1,166 @@
+/* cubemap_b200.h — C ABI of libcubemap_b200.so (B200 / sm_100a hot path of CubemapSLAM).
+ *
+ * The reference has no FFI layer: its "operator API" for this path is four C++ entry points compiled into
+ * libCubemapSLAM.so. Each function below names the reference interface it replaces (file:line in the reference
+ * tree); the facade classes in include/ORBExtractor.h, ORBMatcher.h, Optimizer.h, CubemapWarp.h keep the
+ * reference signatures and forward to these. INTEGRATION.md shows the maintainer-side binding.
+ *
+ * Conventions: every function returns 0 on success or a negative CSLAM_E_* code (cslam_last_error() gives the
+ * text, thread-local); no exceptions cross the ABI; the caller owns every buffer it passes; the library owns
+ * device memory and streams; "_dev" entry points take DEVICE pointers and run asynchronously on the handle's
+ * stream (cslam_*_sync to wait), all others take HOST pointers and are synchronous. There is no CPU fallback:
+ * without a CUDA device creation fails with CSLAM_E_NODEVICE.
+ */
+#ifndef CUBEMAP_B200_H
+#define CUBEMAP_B200_H
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CSLAM_OK 0
+#define CSLAM_E_NODEVICE -1
+#define CSLAM_E_BADARG -2
+#define CSLAM_E_CUDA -3
+#define CSLAM_E_CAPACITY -4   /* an internal fixed-capacity buffer overflowed (reported, never silently truncated) */
+#define CSLAM_E_NCCL -5
+
+const char* cslam_last_error(void);
+int cslam_version(void);
+int cslam_device_count(void);
+
+/* ---------------------------------------------------------------------------------------------- camera / warp
+ * CamModelGeneral::SetCamParams (src/CamModelGeneral.cpp:75-93) as configured by System::System (src/System.cpp:63-89). */
+typedef struct cslam_cam_params {
+    double c, d, e, u0, v0;
+    double poly[5];      /* Camera.a0..a4, zero padded (src/System.cpp:67-69) */
+    double invpoly[12];  /* Camera.pol0..pol11, zero padded (src/System.cpp:70-72) */
+    int32_t Iw, Ih;      /* fisheye image size */
+    int32_t face_w, face_h; /* CubeFace.w/h; fx=fy=cx=cy=w/2 (src/System.cpp:83-84). Must be square. */
+    double fov_deg;
+} cslam_cam_params;
+
+/* cv::KeyPoint field order (28 bytes) — element type of ORBextractor's output vector. */
+typedef struct cslam_keypoint {
+    float x, y, size, angle, response;
+    int32_t octave, class_id;
+} cslam_keypoint;
+
+typedef struct cslam_orb_params {  /* ORBextractor::ORBextractor arguments (src/ORBExtractor.cpp:381-383) */
+    int32_t nfeatures;
+    float scale_factor;
+    int32_t nlevels, ini_th_fast, min_th_fast;
+} cslam_orb_params;
+
+/* Front end = System::CreateUndistortRectifyMap (src/System.cpp:301-324, run once here on the host exactly like the
+ * reference does at start-up) + CvtFisheyeToCubeMap_reverseQuery_withInterpolation (src/System.cpp:327-355)
+ * + ORBextractor::operator() (src/ORBExtractor.cpp:838-926), batched over `max_batch` frames per launch group.
+ * `mask` is the (3*face_h x 3*face_w) CV_8U cubemap mask the reference passes to every Frame (host pointer, copied). */
+typedef struct cslam_frontend cslam_frontend;
+int cslam_frontend_create(cslam_frontend** out, int device, const cslam_cam_params* cam, const cslam_orb_params* orb,
+                          const uint8_t* mask, int mask_pitch, int max_batch);
+void cslam_frontend_destroy(cslam_frontend* fe);
+int cslam_frontend_kp_capacity(const cslam_frontend* fe);   /* per-frame keypoint slots = nfeatures + 3*nlevels */
+void* cslam_frontend_stream(const cslam_frontend* fe);      /* cudaStream_t the _dev calls are enqueued on */
+int cslam_frontend_sync(cslam_frontend* fe);                /* waits, then reports sticky capacity/CUDA errors */
+
+/* System::CvtFisheyeToCubeMap_reverseQuery_withInterpolation(cubemapImg, fisheyeImg, INTER_LINEAR) for `batch`
+ * frames. fisheye: batch x Ih x Iw (pitch Iw); canvas: batch x 3H x canvas_pitch, corner tiles are left untouched. */
+int cslam_warp(cslam_frontend* fe, const uint8_t* fisheye, int batch, uint8_t* canvas, int canvas_pitch);
+/* ORBextractor::operator()(image, mask, keypoints, descriptors) on host cubemap canvases (3H x 3W, given pitch).
+ * kps: batch x kp_capacity; desc: batch x kp_capacity x 32; n_out: batch. */
+int cslam_orb_extract(cslam_frontend* fe, const uint8_t* canvas, int canvas_pitch, int batch, cslam_keypoint* kps,
+                      uint8_t* desc, int32_t* n_out);
+/* warp + extract, host fisheye frames in, host keypoints/descriptors out (copies inside). */
+int cslam_frontend_run(cslam_frontend* fe, const uint8_t* fisheye, int batch, cslam_keypoint* kps, uint8_t* desc,
+                       int32_t* n_out);
+/* Same with device-resident input and output (asynchronous on the front end's stream). */
+int cslam_frontend_run_dev(cslam_frontend* fe, const uint8_t* fisheye_dev, int batch, cslam_keypoint* kps_dev,
+                           uint8_t* desc_dev, int32_t* n_out_dev);
+/* Debug / stage-parity access (host copies of the last batch's intermediates). level image is apron-less. */
+int cslam_frontend_level_size(const cslam_frontend* fe, int level, int* w, int* h);
+int cslam_frontend_get_level(cslam_frontend* fe, int frame, int level, uint8_t* out /* h*w */);
+int cslam_frontend_get_candidates(cslam_frontend* fe, int frame, int level, int32_t* xyr /* cap*3 */, int cap, int* n);
+int cslam_frontend_get_maps(const cslam_frontend* fe, float* map1, float* map2);   /* 3H x 3W float32 each */
+int cslam_frontend_tables(const cslam_frontend* fe, float* scale, float* inv_scale, float* sigma2, float* inv_sigma2,
+                          int32_t* features_per_level, int32_t* umax16);
+/* Number of kernel launches issued by this front end so far (bench.py's gpu_launches). */
+int64_t cslam_frontend_launches(const cslam_frontend* fe);
+
+/* ---------------------------------------------------------------------------------------------- matcher
+ * ORBMatcher (include/ORBMatcher.h:42-104). Thresholds TH_LOW=50, TH_HIGH=100, HISTO_LENGTH=12 (src/ORBMatcher.cpp:42-45). */
+typedef struct cslam_matcher cslam_matcher;
+int cslam_matcher_create(cslam_matcher** out, int device, int max_pairs, int max_features);
+void cslam_matcher_destroy(cslam_matcher* m);
+void* cslam_matcher_stream(const cslam_matcher* m);
+int cslam_matcher_sync(cslam_matcher* m);
+int64_t cslam_matcher_launches(const cslam_matcher* m);
+
+/* ORBMatcher::DescriptorDistance (src/ORBMatcher.cpp:951-967), host-side convenience for n descriptor pairs. */
+int cslam_hamming(cslam_matcher* m, const uint8_t* a, const uint8_t* b, int n, int32_t* dist);
+/* All-pairs matcher (BASELINE config 3; semantics defined in DESIGN.md §matcher — SearchByBoW's acceptance rule and
+ * rotation histogram over all columns, per row of A): descA npairs x nA x 32, angA npairs x nA, same for B.
+ * match12: npairs x nA (column of B or -1); dist12/second12 may be NULL; nmatches: npairs. */
+int cslam_match_bruteforce(cslam_matcher* m, const uint8_t* descA, const float* angA, int nA, const uint8_t* descB,
+                           const float* angB, int nB, int npairs, float nnratio, int th_low, int check_ori,
+                           int32_t* match12, int32_t* dist12, int32_t* second12, int32_t* nmatches);
+int cslam_match_bruteforce_dev(cslam_matcher* m, const uint8_t* descA, const float* angA, int nA, const uint8_t* descB,
+                               const float* angB, int nB, int npairs, float nnratio, int th_low, int check_ori,
+                               int32_t* match12, int32_t* dist12, int32_t* second12, int32_t* nmatches);
+/* ORBMatcher::SearchByBoW(KeyFrame*, Frame&, vector<MapPoint*>&) (src/ORBMatcher.cpp:409-539) for npairs (KF,F) pairs.
+ * kf_valid: 1 where the KF feature has a good MapPoint; node_kf/node_f: DBoW2 FeatureVector node id per feature.
+ * match_f: npairs x nF (index of the KF feature whose MapPoint is assigned, or -1); nmatches: npairs. */
+int cslam_search_by_bow(cslam_matcher* m, const uint8_t* descKF, const float* angKF, const uint8_t* kf_valid,
+                        const int32_t* node_kf, int nKF, const uint8_t* descF, const float* angF, const int32_t* node_f,
+                        int nF, int npairs, float nnratio, int check_ori, int32_t* match_f, int32_t* nmatches);
+int cslam_search_by_bow_dev(cslam_matcher* m, const uint8_t* descKF, const float* angKF, const uint8_t* kf_valid,
+                            const int32_t* node_kf, int nKF, const uint8_t* descF, const float* angF, const int32_t* node_f,
+                            int nF, int npairs, float nnratio, int check_ori, int32_t* match_f, int32_t* nmatches);
+
+/* ---------------------------------------------------------------------------------------------- optimizer
+ * Optimizer::LocalBundleAdjustment (src/Optimizer.cpp:192-451) on the already collected local window.
+ * Vertices must be ordered like g2o orders them: KFs by mnId, points by mnId. */
+typedef struct cslam_ba_problem {
+    int32_t n_kf, n_mp, n_edges;
+    float* Tcw;              /* n_kf x 16 row-major float32 (KeyFrame::GetPose), in/out */
+    const uint8_t* kf_fixed; /* n_kf: mnId==0 or member of lFixedCameras */
+    float* points;           /* n_mp x 3 float32 (MapPoint::GetWorldPos), in/out */
+    const int32_t* edge_mp;  /* n_edges */
+    const int32_t* edge_kf;  /* n_edges */
+    const float* kp_xy;      /* n_edges x 2, keypoint on the cubemap canvas (mvKeys[].pt) */
+    const float* inv_sigma2; /* n_edges, mvInvLevelSigma2[kp.octave] */
+    int32_t face_w, face_h;
+} cslam_ba_problem;
+
+typedef struct cslam_ba_result {
+    uint8_t* outlier;        /* n_edges: observations the reference would erase (src/Optimizer.cpp:403-416); may be NULL */
+    double* pose_fp64;       /* n_kf x 7 (t, qx qy qz qw) before the float32 cast; may be NULL */
+    double* points_fp64;     /* n_mp x 3; may be NULL */
+    double* lm_log;          /* log_cap x 4: chi2, lambda, trials, accepted per LM iteration; may be NULL */
+    int32_t log_cap;
+    int32_t iterations;      /* out: LM iterations run (both optimize() calls) */
+    int32_t trials;          /* out: total LM trials (linear solves) */
+} cslam_ba_result;
+
+typedef struct cslam_optimizer cslam_optimizer;
+int cslam_optimizer_create(cslam_optimizer** out, int device);
+void cslam_optimizer_destroy(cslam_optimizer* o);
+int64_t cslam_optimizer_launches(const cslam_optimizer* o);
+/* Landmark-sharded multi-GPU BA: every rank calls with the SAME problem; rank r owns landmarks l % nranks == r and
+ * all-reduces the reduced camera system over NCCL. id128: ncclUniqueId bytes from cslam_nccl_unique_id on rank 0. */
+int cslam_nccl_unique_id(uint8_t id128[128]);
+int cslam_optimizer_init_nccl(cslam_optimizer* o, const uint8_t id128[128], int rank, int nranks);
+/* its1/its2: iterations of the two optimize() calls (reference: 5 and 10). stop_flag: the reference's pbStopFlag. */
+int cslam_local_ba(cslam_optimizer* o, cslam_ba_problem* p, const volatile uint8_t* stop_flag, int its1, int its2,
+                   cslam_ba_result* r);
+/* Optimizer::PoseOptimization (src/Optimizer.cpp:48-190), batched: `nframes` independent frames, frame f owns
+ * correspondences [offset[f], offset[f+1]). Tcw: nframes x 16 in/out; outlier: per correspondence (mvbOutlier);
+ * inliers: nframes (return value of the reference function). */
+int cslam_pose_optimization(cslam_optimizer* o, int nframes, const int32_t* offset, float* Tcw, const float* Xw,
+                            const float* kp_xy, const float* inv_sigma2, int face_w, int face_h, uint8_t* outlier,
+                            int32_t* inliers, double* pose_fp64);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

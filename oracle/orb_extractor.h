@@ -5,6 +5,8 @@
 //   * quadtree finishing phase sorts by (count, heap pointer) (src/ORBExtractor.cpp:658): the oracle
 //     uses (count, creation sequence number) - "later created = larger address".
 //   * cosf/sinf (src/ORBExtractor.cpp:83-84): det_sincosf (cvprim.h).
+//   * a level whose node list can no longer grow while it is shorter than N/100 makes the reference loop forever
+//     (src/ORBExtractor.cpp:643); here the loop ends (see DistributeOctTree).
 #pragma once
 #include <algorithm>
 #include <cmath>
@@ -209,11 +211,12 @@ public:
         while (!bFinish) {
             int prevSize = (int)lNodes.size();
             lit = lNodes.begin();
-            int nToExpand = 0;
+            int nToExpand = 0, nDivided = 0;
             vSizeAndPointerToNode.clear();
             while (lit != lNodes.end()) {
                 if (lit->bNoMore) { lit++; continue; }
                 ExtractorNode n1, n2, n3, n4;
+                nDivided++;
                 lit->DivideNode(n1, n2, n3, n4);
                 pushChild(n1, vSizeAndPointerToNode, &nToExpand);
                 pushChild(n2, vSizeAndPointerToNode, &nToExpand);
@@ -222,6 +225,11 @@ public:
                 lit = lNodes.erase(lit);
             }
             if ((int)lNodes.size() >= N || ((int)lNodes.size() == prevSize && (int)lNodes.size() >= N / 100)) {
+                bFinish = true;
+            } else if (nDivided == 0) {
+                // DEFINED BEHAVIOUR: with fewer than N/100 nodes and nothing left to divide (e.g. a level without any
+                // FAST corner) the reference's modified stop rule (src/ORBExtractor.cpp:643) never becomes true and
+                // the loop spins forever. The oracle (and the CUDA path) stop here with the current nodes.
                 bFinish = true;
             } else if (((int)lNodes.size() + nToExpand * 3) > N) {
                 while (!bFinish) {

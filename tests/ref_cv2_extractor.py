@@ -66,14 +66,17 @@ def distribute(keys, minX, maxX, minY, maxY, N):
     while not finish:
         prev = len(nodes)
         work = [n for n in nodes]
-        rec = []; cnt = [0]
+        rec = []; cnt = [0]; ndiv = 0
         for n in work:
             if n.nomore:
                 continue
+            ndiv += 1
             push(divide(n), rec, cnt)
             nodes.remove(n)
         if len(nodes) >= N or (len(nodes) == prev and len(nodes) >= N // 100):
             finish = True
+        elif ndiv == 0:
+            finish = True      # defined behaviour (the reference would spin forever), see oracle/orb_extractor.h
         elif len(nodes) + cnt[0] * 3 > N:
             while not finish:
                 prev = len(nodes)
