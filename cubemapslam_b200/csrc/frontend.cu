@@ -153,19 +153,25 @@ __device__ __forceinline__ int fast_score(const uint8_t* t, int minTh) {
 #pragma unroll
     for (int k = 0; k < 16; k++) { hi |= (uint32_t)(d[k] > minTh) << k; lo |= (uint32_t)(d[k] < -minTh) << k; }
     if (!arc9_mask(hi) && !arc9_mask(lo)) return 0;
-    // exact score: sliding min/max over 9 contiguous (doubling: 2,4,8,+1)
-    int mn[16], mx[16];
+    // exact score: sliding min over 9 contiguous ring pixels (doubling: 2,4,8,+1) of d and of e=-d.
+    // (Written with two min-trees and no negated operand inside the max: nvcc 12.9 mis-fuses max(a,-b) of a
+    //  3-input max tree into VIMNMX3 on sm_100a, found with tools/dbg_fast.cu.)
+    int e[16];
 #pragma unroll
-    for (int k = 0; k < 16; k++) { mn[k] = min(d[k], d[(k + 1) & 15]); mx[k] = max(d[k], d[(k + 1) & 15]); }
-    int mn4[16], mx4[16];
+    for (int k = 0; k < 16; k++) e[k] = -d[k];
+    int mn[16], me[16];
 #pragma unroll
-    for (int k = 0; k < 16; k++) { mn4[k] = min(mn[k], mn[(k + 2) & 15]); mx4[k] = max(mx[k], mx[(k + 2) & 15]); }
+    for (int k = 0; k < 16; k++) { mn[k] = min(d[k], d[(k + 1) & 15]); me[k] = min(e[k], e[(k + 1) & 15]); }
+    int mn4[16], me4[16];
+#pragma unroll
+    for (int k = 0; k < 16; k++) { mn4[k] = min(mn[k], mn[(k + 2) & 15]); me4[k] = min(me[k], me[(k + 2) & 15]); }
     int best = 0;
 #pragma unroll
     for (int k = 0; k < 16; k++) {
         const int a = min(min(mn4[k], mn4[(k + 4) & 15]), d[(k + 8) & 15]);
-        const int b = max(max(mx4[k], mx4[(k + 4) & 15]), d[(k + 8) & 15]);
-        best = max(best, max(a, -b));
+        const int b = min(min(me4[k], me4[(k + 4) & 15]), e[(k + 8) & 15]);
+        best = max(best, a);
+        best = max(best, b);
     }
     return best;
 }
@@ -207,6 +213,14 @@ __global__ void __launch_bounds__(256) k_fast(const uint8_t* __restrict__ img, L
     for (int i = tid; i < nx * ny; i += blockDim.x) {
         const int y = i / nx, x = i - y * nx;
         S[(y + 1) * SS + x + 1] = (uint8_t)fast_score(tile + (y + 3) * FAST_TS + xoff + x, minTh);
+#ifdef CSLAM_DEBUG_FAST
+        if (blockIdx.x == 0 && blockIdx.y == 0 && x == 0 && y == 29) {
+            const uint8_t* t = tile + (y + 3) * FAST_TS + xoff + x;
+            printf("dev pixel c=%d ring: %d %d %d %d %d %d %d %d %d %d %d %d %d %d %d %d score=%d (a0=%d tx0=%d xoff=%d nwords=%d nrows=%d)\n", t[0], t[-3 * FAST_TS], t[-3 * FAST_TS + 1],
+                   t[-2 * FAST_TS + 2], t[-FAST_TS + 3], t[3], t[FAST_TS + 3], t[2 * FAST_TS + 2], t[3 * FAST_TS + 1], t[3 * FAST_TS], t[3 * FAST_TS - 1],
+                   t[2 * FAST_TS - 2], t[FAST_TS - 3], t[-3], t[-FAST_TS - 3], t[-2 * FAST_TS - 2], t[-3 * FAST_TS - 1], (int)S[(y + 1) * SS + x + 1], a0, tx0, xoff, nwords, nrows);
+        }
+#endif
     }
     __syncthreads();
     // keypoint test for threshold T: s > T and no same-cell neighbour n with s_n > T and s_n >= s

@@ -42,7 +42,7 @@ def test_warp_bit_exact(oracle, lafida):
         assert np.array_equal(got[i], oracle.warp(cp, frames[i], m1, m2)), "frame %d" % i
     # corner tiles of a caller-provided canvas stay untouched
     canvas = np.full((1350, 1350), 7, np.uint8)
-    out = fe.warp(frames[0], canvas[None].copy())[0]
+    out = fe.warp(frames[0], canvas[None].copy())
     assert np.all(out[:450, :450] == 7) and np.all(out[900:, 900:] == 7) and np.array_equal(out[450:900], got[0][450:900])
 
 
