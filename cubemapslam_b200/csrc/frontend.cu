@@ -657,9 +657,28 @@ struct cslam_frontend {
     std::vector<void*> owned;
     int64_t launches = 0;
     int lastBatch = 0;
+    // optional per-kernel timing (cslam_frontend_set_timing): events between launches, accumulated per kernel kind
+    bool timing = false; std::vector<cudaEvent_t> ev; std::vector<int> evKind; int evUsed = 0;
+    double kindMs[8] = {0, 0, 0, 0, 0, 0, 0, 0}; int64_t kindCount[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     bool cornersDirty = false;   // level-0 buffer holds caller canvases (non-zero corner tiles) from cslam_orb_extract
     size_t distributeSmem = 0;
 };
+
+enum { KIND_WARP = 0, KIND_PYRAMID, KIND_FAST, KIND_DISTRIBUTE, KIND_DESCRIBE, KIND_END, KIND_COUNT };
+static const char* kKindNames[KIND_COUNT] = {"k_warp", "k_pyramid", "k_fast", "k_distribute", "k_describe", "end"};
+static inline void mark(cslam_frontend* fe, int kind) {
+    if (kind != KIND_END) fe->launches++;
+    if (!fe->timing || fe->evUsed >= (int)fe->ev.size()) return;
+    cudaEventRecord(fe->ev[fe->evUsed], fe->stream);
+    fe->evKind[fe->evUsed++] = kind;
+}
+static void collect_timing(cslam_frontend* fe) {
+    for (int i = 0; i + 1 < fe->evUsed; i++) {
+        float ms = 0;
+        if (cudaEventElapsedTime(&ms, fe->ev[i], fe->ev[i + 1]) == cudaSuccess) { fe->kindMs[fe->evKind[i]] += ms; fe->kindCount[fe->evKind[i]]++; }
+    }
+    fe->evUsed = 0;
+}
 
 static inline int cv_round_f(float v) { return (int)lrintf(v); }
 static inline int cv_round_d(double v) { return (int)lrint(v); }
@@ -851,6 +870,7 @@ extern "C" void cslam_frontend_destroy(cslam_frontend* fe) {
     cudaSetDevice(fe->device);
     if (fe->stream) { cudaStreamSynchronize(fe->stream); cudaStreamDestroy(fe->stream); }
     for (void* p : fe->owned) cudaFree(p);
+    for (auto& e : fe->ev) cudaEventDestroy(e);
     if (fe->h_pin_in) cudaFreeHost(fe->h_pin_in);
     if (fe->h_pin_kps) cudaFreeHost(fe->h_pin_kps);
     if (fe->h_pin_desc) cudaFreeHost(fe->h_pin_desc);
@@ -859,6 +879,22 @@ extern "C" void cslam_frontend_destroy(cslam_frontend* fe) {
     delete fe;
 }
 
+extern "C" int cslam_frontend_set_timing(cslam_frontend* fe, int enable) {
+    if (!fe) return CSLAM_E_BADARG;
+    CSLAM_CUDA(cudaSetDevice(fe->device));
+    if (enable && fe->ev.empty()) {
+        fe->ev.resize(256); fe->evKind.resize(256);
+        for (auto& e : fe->ev) CSLAM_CUDA(cudaEventCreate(&e));
+    }
+    fe->timing = enable != 0; fe->evUsed = 0;
+    for (int i = 0; i < 8; i++) { fe->kindMs[i] = 0; fe->kindCount[i] = 0; }
+    return CSLAM_OK;
+}
+extern "C" int cslam_frontend_get_timing(const cslam_frontend* fe, int kind, const char** name, double* ms, int64_t* count) {
+    if (!fe || kind < 0 || kind >= KIND_END) return CSLAM_E_BADARG;
+    *name = kKindNames[kind]; *ms = fe->kindMs[kind]; *count = fe->kindCount[kind];
+    return CSLAM_OK;
+}
 extern "C" int cslam_frontend_kp_capacity(const cslam_frontend* fe) { return fe ? fe->kpCap : 0; }
 extern "C" void* cslam_frontend_stream(const cslam_frontend* fe) { return fe ? (void*)fe->stream : nullptr; }
 extern "C" int64_t cslam_frontend_launches(const cslam_frontend* fe) { return fe ? fe->launches : 0; }
@@ -867,6 +903,7 @@ extern "C" int cslam_frontend_sync(cslam_frontend* fe) {
     if (!fe) return CSLAM_E_BADARG;
     CSLAM_CUDA(cudaMemcpyAsync(fe->h_pin_err, fe->d_err, sizeof(int), cudaMemcpyDeviceToHost, fe->stream));
     CSLAM_CUDA(cudaStreamSynchronize(fe->stream));
+    if (fe->timing) collect_timing(fe);
     if (*fe->h_pin_err != 0) {
         const int code = *fe->h_pin_err;
         cudaMemsetAsync(fe->d_err, 0, sizeof(int), fe->stream);
@@ -883,9 +920,9 @@ static int launch_warp(cslam_frontend* fe, const uint8_t* d_fisheye, int batch) 
         fe->cornersDirty = false;
     }
     dim3 grid(cdiv(fe->W, 256), fe->H, 5 * cdiv(batch, FPT));
+    mark(fe, KIND_WARP);
     k_warp<FPT><<<grid, 256, 0, fe->stream>>>(d_fisheye, fe->cam.Iw, fe->cam.Ih, fe->d_map, fe->W, fe->L.img[0], fe->L.g[0].pitch,
                                                (size_t)fe->L.g[0].pitch * fe->CH, batch);
-    fe->launches++;
     CSLAM_CUDA(cudaGetLastError());
     return 0;
 }
@@ -897,26 +934,27 @@ static int launch_extract(cslam_frontend* fe, int batch, cslam_keypoint* d_kps, 
     for (int l = 1; l < nl; l++) {
         const LevelGeom& s = fe->L.g[l - 1]; const LevelGeom& d = fe->L.g[l];
         dim3 grid(cdiv(cdiv(d.w, 4), 256), d.h, batch);
+        mark(fe, KIND_PYRAMID);
         k_pyramid<<<grid, 256, 0, fe->stream>>>(fe->L.img[l - 1], s.w, s.h, s.pitch, fe->L.img[l], d.w, d.h, d.pitch, fe->L.xofs[l], fe->L.xab[l], fe->L.yofs[l], fe->L.yab[l]);
-        fe->launches++;
     }
     for (int l = 0; l < nl; l++) {
         const LevelGeom& g = fe->L.g[l];
         dim3 grid(cdiv(g.nColsEff, CG), g.nRowsEff, batch);
+        mark(fe, KIND_FAST);
         k_fast<<<grid, 256, 0, fe->stream>>>(fe->L.img[l], g, fe->orb.ini_th_fast, fe->orb.min_th_fast, fe->L.cand[l], fe->d_candCount + l, nl, fe->d_err);
-        fe->launches++;
     }
     CSLAM_CUDA(cudaGetLastError());
     DistributeArgs da;
     da.L = fe->L; da.candCount = fe->d_candCount; da.kept = fe->d_kept; da.keptCount = fe->d_keptCount; da.mask = fe->d_mask; da.maskPitch = fe->maskPitch;
     da.imgW = fe->CW; da.imgH = fe->CH; da.faceW = fe->W; da.faceH = fe->H; da.keptCap = fe->keptCap; da.M = fe->M; da.errFlag = fe->d_err;
+    mark(fe, KIND_DISTRIBUTE);
     k_distribute<<<dim3(nl, batch), 256, fe->distributeSmem, fe->stream>>>(da);
-    fe->launches++;
     DescribeArgs ds;
     ds.L = fe->L; ds.kept = fe->d_kept; ds.keptCount = fe->d_keptCount; ds.keptCap = fe->keptCap; ds.kps = d_kps; ds.desc = d_desc; ds.nOut = d_nout; ds.kpCap = fe->kpCap;
     ds.errFlag = fe->d_err;
+    mark(fe, KIND_DESCRIBE);
     k_describe<<<dim3(cdiv(fe->keptCap, DESC_WARPS), nl, batch), DESC_WARPS * 32, 0, fe->stream>>>(ds);
-    fe->launches++;
+    mark(fe, KIND_END);
     CSLAM_CUDA(cudaGetLastError());
     return 0;
 }

@@ -91,6 +91,17 @@ class FrontEnd:
     def launches(self):
         return lib().cslam_frontend_launches(self._h)
 
+    def set_timing(self, enable):
+        check(lib().cslam_frontend_set_timing(self._h, int(enable)))
+
+    def timing(self):
+        out = {}
+        for kind in range(5):
+            name = C.c_char_p(); ms = C.c_double(); cnt = C.c_int64()
+            check(lib().cslam_frontend_get_timing(self._h, kind, C.byref(name), C.byref(ms), C.byref(cnt)))
+            out[name.value.decode()] = (ms.value, cnt.value)
+        return out
+
     # ---- stage access for parity tests
     def level_image(self, frame, level):
         w = C.c_int(); h = C.c_int()

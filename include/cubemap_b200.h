@@ -84,6 +84,11 @@ int cslam_frontend_get_candidates(cslam_frontend* fe, int frame, int level, int3
 int cslam_frontend_get_maps(const cslam_frontend* fe, float* map1, float* map2);   /* 3H x 3W float32 each */
 int cslam_frontend_tables(const cslam_frontend* fe, float* scale, float* inv_scale, float* sigma2, float* inv_sigma2,
                           int32_t* features_per_level, int32_t* umax16);
+/* Per-kernel device timing for bench.py's roofline block: when enabled, CUDA events are recorded on the front end's
+ * stream between launches and accumulated per kernel kind at the next cslam_frontend_sync. kind 0..4 =
+ * k_warp, k_pyramid, k_fast, k_distribute, k_describe. */
+int cslam_frontend_set_timing(cslam_frontend* fe, int enable);
+int cslam_frontend_get_timing(const cslam_frontend* fe, int kind, const char** name, double* ms, int64_t* count);
 /* Number of kernel launches issued by this front end so far (bench.py's gpu_launches). */
 int64_t cslam_frontend_launches(const cslam_frontend* fe);
 
