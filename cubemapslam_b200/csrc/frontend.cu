@@ -132,140 +132,190 @@ __global__ void __launch_bounds__(256) k_pyramid(const uint8_t* __restrict__ src
 // corner(thr) <=> s > thr; OpenCV response = s-1. The reference runs cv::FAST per cell ROI [ini, ini+cell+6):
 // detection areas of neighbouring cells tile the level without overlap, NMS only sees scores of the same cell,
 // and the 20->7 fallback is decided per cell on "no keypoint survived NMS" (src/ORBExtractor.cpp:763-803).
-__device__ __forceinline__ int arc9_mask(uint32_t m) {   // m: 16-bit ring mask; non-zero iff 9 contiguous bits (cyclic)
-    m |= m << 16;
-    uint32_t a = m & (m >> 1);
-    a &= a >> 2;
-    a &= a >> 4;
-    a &= m >> 8;
-    return a & 0xffff;
-}
-
-__device__ __forceinline__ int fast_score(const uint8_t* t, int minTh) {
-    // ring offsets clockwise from (0,-3)
-    const int c = t[0];
-    int d[16];
-    d[0] = c - t[-3 * FAST_TS + 0];  d[1] = c - t[-3 * FAST_TS + 1];  d[2] = c - t[-2 * FAST_TS + 2];  d[3] = c - t[-1 * FAST_TS + 3];
-    d[4] = c - t[3];                 d[5] = c - t[1 * FAST_TS + 3];   d[6] = c - t[2 * FAST_TS + 2];   d[7] = c - t[3 * FAST_TS + 1];
-    d[8] = c - t[3 * FAST_TS + 0];   d[9] = c - t[3 * FAST_TS - 1];   d[10] = c - t[2 * FAST_TS - 2];  d[11] = c - t[1 * FAST_TS - 3];
-    d[12] = c - t[-3];               d[13] = c - t[-1 * FAST_TS - 3]; d[14] = c - t[-2 * FAST_TS - 2]; d[15] = c - t[-3 * FAST_TS - 1];
-    uint32_t hi = 0, lo = 0;
-#pragma unroll
-    for (int k = 0; k < 16; k++) { hi |= (uint32_t)(d[k] > minTh) << k; lo |= (uint32_t)(d[k] < -minTh) << k; }
-    if (!arc9_mask(hi) && !arc9_mask(lo)) return 0;
-    // exact score: sliding min over 9 contiguous ring pixels (doubling: 2,4,8,+1) of d and of e=-d.
-    // (Written with two min-trees and no negated operand inside the max: nvcc 12.9 mis-fuses max(a,-b) of a
-    //  3-input max tree into VIMNMX3 on sm_100a, found with tools/dbg_fast.cu.)
-    int e[16];
-#pragma unroll
-    for (int k = 0; k < 16; k++) e[k] = -d[k];
-    int mn[16], me[16];
-#pragma unroll
-    for (int k = 0; k < 16; k++) { mn[k] = min(d[k], d[(k + 1) & 15]); me[k] = min(e[k], e[(k + 1) & 15]); }
-    int mn4[16], me4[16];
-#pragma unroll
-    for (int k = 0; k < 16; k++) { mn4[k] = min(mn[k], mn[(k + 2) & 15]); me4[k] = min(me[k], me[(k + 2) & 15]); }
-    int best = 0;
+// Exact arc score of 2 horizontally adjacent pixels at once in u16x2 lanes (sm_100a VIMNMX3.U16x2):
+//   s = max(0, A - c, c - B),  A = max_k min(R[k..k+8]),  B = min_k max(R[k..k+8])   (R = ring intensities, c = centre)
+// min/max over 9 contiguous ring pixels = min3 of three min3's. No data-dependent branch, no per-pixel early-out:
+// on textured input almost every pixel passes the cheap antipodal tests, so the branch-free full score is cheaper
+// than queueing (measured with ncu: profiles/r01_k_fast_*.txt).
+__device__ __forceinline__ uint32_t arc_score_x2(const uint32_t (&R)[16], uint32_t c) {
+    uint32_t mn[16], mx[16];
 #pragma unroll
     for (int k = 0; k < 16; k++) {
-        const int a = min(min(mn4[k], mn4[(k + 4) & 15]), d[(k + 8) & 15]);
-        const int b = min(min(me4[k], me4[(k + 4) & 15]), e[(k + 8) & 15]);
-        best = max(best, a);
-        best = max(best, b);
+        mn[k] = __vimin3_u16x2(R[k], R[(k + 1) & 15], R[(k + 2) & 15]);
+        mx[k] = __vimax3_u16x2(R[k], R[(k + 1) & 15], R[(k + 2) & 15]);
     }
-    return best;
+    uint32_t A = 0u, Bm = 0xffffffffu;
+#pragma unroll
+    for (int k = 0; k < 16; k += 2) {
+        const uint32_t a0 = __vimin3_u16x2(mn[k], mn[(k + 3) & 15], mn[(k + 6) & 15]);
+        const uint32_t a1 = __vimin3_u16x2(mn[k + 1], mn[(k + 4) & 15], mn[(k + 7) & 15]);
+        const uint32_t b0 = __vimax3_u16x2(mx[k], mx[(k + 3) & 15], mx[(k + 6) & 15]);
+        const uint32_t b1 = __vimax3_u16x2(mx[k + 1], mx[(k + 4) & 15], mx[(k + 7) & 15]);
+        A = __vimax3_u16x2(A, a0, a1);
+        Bm = __vimin3_u16x2(Bm, b0, b1);
+    }
+    const uint32_t t1 = __vmaxu2(A, c) - c;      // lanes never borrow: max(A,c) >= c
+    const uint32_t t2 = c - __vminu2(Bm, c);
+    return __vmaxu2(t1, t2);
 }
 
+// Layout of one CTA: CG cells of one cell row. Phases:
+//  A  branch-free exact arc score of every detection pixel (4 pixels per work item) -> S (u8, 0 where s <= minTh)
+//  B  3x3 NMS at minTh inside each cell -> shared list; a keypoint at iniTh is exactly an NMS survivor with s > iniTh
+//     (a suppressor needs s_n >= s), so the per-cell 20->7 fallback is a filter on that list
+//  C  compaction of the selected entries into the global candidate list (one global atomic per 256 entries)
+static const int FAST_KMAX = CG * (CELL_MAX / 2) * (CELL_MAX / 2);   // NMS survivors are pairwise non-adjacent
+
 __global__ void __launch_bounds__(256) k_fast(const uint8_t* __restrict__ img, LevelGeom g, int iniTh, int minTh, uint32_t* __restrict__ cand,
-                                              uint32_t* __restrict__ candCount, int countStride, int* __restrict__ errFlag) {
+                                              uint32_t* __restrict__ candCount, int countStride, int* __restrict__ errFlag,
+                                              const uint8_t* __restrict__ skip) {
     __shared__ __align__(16) uint8_t tile[FAST_TH * FAST_TS];
-    __shared__ uint8_t S[(CELL_MAX + 2) * (CG * CELL_MAX + 2)];
+    __shared__ __align__(16) uint8_t S[(CELL_MAX + 2) * FAST_TS];   // same column addressing as `tile`, row y+1
+    __shared__ uint32_t klist[FAST_KMAX];                            // x | y<<8 | s<<16 | cell<<24
+    __shared__ uint8_t cellInfo[FAST_TS];   // per detection column: cell index | 0x40 first column of its cell | 0x80 last
     __shared__ int cnt20[CG];
-    __shared__ int anyNonZero;
+    __shared__ int anyNonZero, nK, chunkBase;
+    __shared__ int warpCnt[8];
     const int frame = blockIdx.z, cellRow = blockIdx.y, j0 = blockIdx.x * CG;
-    const int tid = threadIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (skip && skip[cellRow * gridDim.x + blockIdx.x]) return;   // tile provably all-zero (black cubemap corner)
     const uint8_t* I = img + (size_t)frame * g.pitch * g.h;
     const int iniY = g.minB + cellRow * g.hCell, maxY = min(iniY + g.hCell + 6, g.maxBY);
     const int ncell = min(CG, g.nColsEff - j0);
     const int tx0 = g.minB + j0 * g.wCell, tx1 = min(tx0 + ncell * g.wCell + 6, g.maxBX);
     const int a0 = tx0 & ~3, nwords = (tx1 - a0 + 3) >> 2, nrows = maxY - iniY;
     if (tid < CG) cnt20[tid] = 0;
-    if (tid == 0) anyNonZero = 0;
+    if (tid == 0) { anyNonZero = 0; nK = 0; }
     __syncthreads();
     uint32_t acc = 0;
-    for (int i = tid; i < nwords * nrows; i += blockDim.x) {
-        const int r = i / nwords, wd = i - r * nwords;
-        const uint32_t v = __ldg(reinterpret_cast<const uint32_t*>(I + (size_t)(iniY + r) * g.pitch + a0) + wd);
-        *reinterpret_cast<uint32_t*>(tile + r * FAST_TS + wd * 4) = v;
-        acc |= v;
+    for (int r = warp; r < nrows; r += 8) {
+        const uint32_t* src = reinterpret_cast<const uint32_t*>(I + (size_t)(iniY + r) * g.pitch + a0);
+        uint32_t* dst = reinterpret_cast<uint32_t*>(tile + r * FAST_TS);
+        for (int wd = lane; wd < nwords; wd += 32) { const uint32_t v = __ldg(src + wd); dst[wd] = v; acc |= v; }
     }
     if (acc) anyNonZero = 1;
-    __syncthreads();
-    if (!anyNonZero) return;   // an all-zero tile (black cubemap corner) has no corners at any threshold
     const int nx = tx1 - tx0 - 6, ny = nrows - 6;   // detection area
-    if (nx <= 0 || ny <= 0) return;
-    const int SS = nx + 2;
-    for (int i = tid; i < SS * (ny + 2); i += blockDim.x) {
-        const int yy = i / SS, xx = i - yy * SS;
-        if (yy == 0 || yy == ny + 1 || xx == 0 || xx == nx + 1) S[i] = 0;
-    }
-    const int xoff = tx0 - a0 + 3;
-    for (int i = tid; i < nx * ny; i += blockDim.x) {
-        const int y = i / nx, x = i - y * nx;
-        S[(y + 1) * SS + x + 1] = (uint8_t)fast_score(tile + (y + 3) * FAST_TS + xoff + x, minTh);
-#ifdef CSLAM_DEBUG_FAST
-        if (blockIdx.x == 0 && blockIdx.y == 0 && x == 0 && y == 29) {
-            const uint8_t* t = tile + (y + 3) * FAST_TS + xoff + x;
-            printf("dev pixel c=%d ring: %d %d %d %d %d %d %d %d %d %d %d %d %d %d %d %d score=%d (a0=%d tx0=%d xoff=%d nwords=%d nrows=%d)\n", t[0], t[-3 * FAST_TS], t[-3 * FAST_TS + 1],
-                   t[-2 * FAST_TS + 2], t[-FAST_TS + 3], t[3], t[FAST_TS + 3], t[2 * FAST_TS + 2], t[3 * FAST_TS + 1], t[3 * FAST_TS], t[3 * FAST_TS - 1],
-                   t[2 * FAST_TS - 2], t[FAST_TS - 3], t[-3], t[-FAST_TS - 3], t[-2 * FAST_TS - 2], t[-3 * FAST_TS - 1], (int)S[(y + 1) * SS + x + 1], a0, tx0, xoff, nwords, nrows);
-        }
-#endif
+    const int xoff = tx0 - a0 + 3;                   // tile column of detection x = 0
+    for (int i = tid; i < (ny + 2) * (FAST_TS / 4); i += 256) reinterpret_cast<uint32_t*>(S)[i] = 0;
+    for (int x = tid; x < nx; x += 256) {
+        const int c = x / g.wCell, xl = x - c * g.wCell;
+        cellInfo[x] = (uint8_t)(c | (xl == 0 ? 0x40 : 0) | ((xl == g.wCell - 1 || x == nx - 1) ? 0x80 : 0));
     }
     __syncthreads();
-    // keypoint test for threshold T: s > T and no same-cell neighbour n with s_n > T and s_n >= s
-    auto is_kp = [&](int x, int y, int T) -> bool {
-        const uint8_t* c = S + (y + 1) * SS + x + 1;
-        const int s = c[0];
-        if (s <= T) return false;
-        const int xl = x % g.wCell;
-        const bool lok = xl != 0, rok = (xl != g.wCell - 1);
-        int m = max(c[-SS], c[SS]);
-        if (lok) m = max(m, max(c[-1], max(c[-SS - 1], c[SS - 1])));
-        if (rok) m = max(m, max(c[1], max(c[-SS + 1], c[SS + 1])));
-        return !(m > T && m >= s);
-    };
-    for (int i = tid; i < nx * ny; i += blockDim.x) {
-        const int y = i / nx, x = i - y * nx;
-        if (is_kp(x, y, iniTh)) atomicAdd(&cnt20[x / g.wCell], 1);
+    if (!anyNonZero || nx <= 0 || ny <= 0) return;   // an all-zero tile has no corners at any threshold
+    // ---- A
+    {
+        const int w0 = xoff >> 2, w1 = (xoff + nx + 3) >> 2, nw = w1 - w0;
+        const int nitems = nw * ny;
+        for (int it = tid; it < nitems; it += 256) {
+            const int y = it / nw, wi = w0 + (it - y * nw);
+            const uint32_t* r0 = reinterpret_cast<const uint32_t*>(tile + y * FAST_TS) + wi;   // row y-3 relative to the centre row
+            const int RS = FAST_TS / 4;
+            uint32_t V[16];
+            {   // dy=-3: ring 15 (dx-1), 0 (dx 0), 1 (dx+1)
+                const uint32_t m = wi > 0 ? r0[-1] : 0u, c = r0[0], p = r0[1];
+                V[15] = __funnelshift_r(m, c, 24); V[0] = c; V[1] = __funnelshift_r(c, p, 8);
+            }
+            {   // dy=-2: ring 14 (dx-2), 2 (dx+2)
+                const uint32_t* r = r0 + RS; const uint32_t m = wi > 0 ? r[-1] : 0u, c = r[0], p = r[1];
+                V[14] = __funnelshift_r(m, c, 16); V[2] = __funnelshift_r(c, p, 16);
+            }
+            {   // dy=-1: ring 13 (dx-3), 3 (dx+3)
+                const uint32_t* r = r0 + 2 * RS; const uint32_t m = wi > 0 ? r[-1] : 0u, c = r[0], p = r[1];
+                V[13] = __funnelshift_r(m, c, 8); V[3] = __funnelshift_r(c, p, 24);
+            }
+            uint32_t C;
+            {   // dy=0: ring 12 (dx-3), 4 (dx+3), centre
+                const uint32_t* r = r0 + 3 * RS; const uint32_t m = wi > 0 ? r[-1] : 0u, c = r[0], p = r[1];
+                V[12] = __funnelshift_r(m, c, 8); V[4] = __funnelshift_r(c, p, 24); C = c;
+            }
+            {   // dy=+1: ring 11 (dx-3), 5 (dx+3)
+                const uint32_t* r = r0 + 4 * RS; const uint32_t m = wi > 0 ? r[-1] : 0u, c = r[0], p = r[1];
+                V[11] = __funnelshift_r(m, c, 8); V[5] = __funnelshift_r(c, p, 24);
+            }
+            {   // dy=+2: ring 10 (dx-2), 6 (dx+2)
+                const uint32_t* r = r0 + 5 * RS; const uint32_t m = wi > 0 ? r[-1] : 0u, c = r[0], p = r[1];
+                V[10] = __funnelshift_r(m, c, 16); V[6] = __funnelshift_r(c, p, 16);
+            }
+            {   // dy=+3: ring 9 (dx-1), 8 (dx 0), 7 (dx+1)
+                const uint32_t* r = r0 + 6 * RS; const uint32_t m = wi > 0 ? r[-1] : 0u, c = r[0], p = r[1];
+                V[9] = __funnelshift_r(m, c, 24); V[8] = c; V[7] = __funnelshift_r(c, p, 8);
+            }
+            uint32_t R[16];
+#pragma unroll
+            for (int k = 0; k < 16; k++) R[k] = __byte_perm(V[k], 0u, 0x4140);
+            const uint32_t sA = arc_score_x2(R, __byte_perm(C, 0u, 0x4140));
+#pragma unroll
+            for (int k = 0; k < 16; k++) R[k] = __byte_perm(V[k], 0u, 0x4342);
+            const uint32_t sB = arc_score_x2(R, __byte_perm(C, 0u, 0x4342));
+            const int c0 = wi * 4 - xoff;   // detection x of byte 0
+            uint32_t sc[4] = {sA & 0xffffu, sA >> 16, sB & 0xffffu, sB >> 16};
+            uint32_t outw = 0;
+#pragma unroll
+            for (int bq = 0; bq < 4; bq++)
+                if ((int)sc[bq] > minTh && (unsigned)(c0 + bq) < (unsigned)nx) outw |= sc[bq] << (8 * bq);
+            reinterpret_cast<uint32_t*>(S + (y + 1) * FAST_TS)[wi] = outw;
+        }
     }
     __syncthreads();
-    uint32_t* out = cand + (size_t)frame * g.candCap;
-    uint32_t* cc = candCount + (size_t)frame * countStride;
-    const int niter = (nx * ny + blockDim.x - 1) / blockDim.x;
-    for (int it = 0; it < niter; it++) {
-        const int i = it * blockDim.x + tid;
-        bool kp = false; int x = 0, y = 0;
-        if (i < nx * ny) {
-            y = i / nx; x = i - y * nx;
-            kp = is_kp(x, y, cnt20[x / g.wCell] > 0 ? iniTh : minTh);
-        }
-        const unsigned ball = __ballot_sync(0xffffffffu, kp);
-        if (ball) {
-            const int lane = tid & 31, leader = __ffs(ball) - 1;
-            uint32_t base = 0;
-            if (lane == leader) base = atomicAdd(cc, __popc(ball));
-            base = __shfl_sync(0xffffffffu, base, leader);
-            if (kp) {
-                const uint32_t pos = base + __popc(ball & ((1u << lane) - 1));
-                if (pos < (uint32_t)g.candCap) {
-                    const uint32_t X = tx0 + 3 + x - g.minB, Y = iniY + 3 + y - g.minB;
-                    out[pos] = X | (Y << 12) | ((uint32_t)(S[(y + 1) * SS + x + 1] - 1) << 24);
-                } else {
-                    *errFlag = CSLAM_E_CAPACITY;
+    // ---- B: NMS at minTh: keep s iff no same-cell neighbour n with s_n >= s (all stored scores are > minTh)
+    {
+        const int w0 = xoff >> 2, w1 = (xoff + nx + 3) >> 2, nw = w1 - w0;
+        const int nitems = nw * ny;
+        for (int it = tid; it < nitems; it += 256) {
+            const int y = it / nw, wi = w0 + (it - y * nw);
+            uint32_t wv = reinterpret_cast<const uint32_t*>(S + (y + 1) * FAST_TS)[wi];
+            while (wv) {
+                const int bq = (__ffs(wv) - 1) >> 3;
+                const int sv = (wv >> (8 * bq)) & 0xff, col = wi * 4 + bq, x = col - xoff;
+                wv &= ~(0xffu << (8 * bq));
+                const uint8_t* c = S + (y + 1) * FAST_TS + col;
+                const int info = cellInfo[x];
+                int m = max(c[-FAST_TS], c[FAST_TS]);
+                if (!(info & 0x40)) m = max(m, max(c[-1], max(c[-FAST_TS - 1], c[FAST_TS - 1])));
+                if (!(info & 0x80)) m = max(m, max(c[1], max(c[-FAST_TS + 1], c[FAST_TS + 1])));
+                if (m < sv) {
+                    const int cell = info & 0x3f;
+                    const int pos = atomicAdd(&nK, 1);
+                    if (pos >= FAST_KMAX) *errFlag = CSLAM_E_CAPACITY;
+                    else klist[pos] = (uint32_t)x | ((uint32_t)y << 8) | ((uint32_t)sv << 16) | ((uint32_t)cell << 24);
+                    if (sv > iniTh) atomicAdd(&cnt20[cell], 1);
                 }
             }
         }
+    }
+    __syncthreads();
+    // ---- C
+    uint32_t* out = cand + (size_t)frame * g.candCap;
+    uint32_t* cc = candCount + (size_t)frame * countStride;
+    const int nk = min(nK, FAST_KMAX);
+    for (int base = 0; base < nk; base += 256) {
+        const int i = base + tid;
+        uint32_t e = 0; bool sel = false;
+        if (i < nk) {
+            e = klist[i];
+            const int sv = (e >> 16) & 0xff, cell = e >> 24;
+            sel = cnt20[cell] > 0 ? sv > iniTh : true;
+        }
+        const unsigned ball = __ballot_sync(0xffffffffu, sel);
+        if (lane == 0) warpCnt[warp] = __popc(ball);
+        __syncthreads();
+        if (tid == 0) {
+            int tot = 0;
+            for (int w = 0; w < 8; w++) { const int t = warpCnt[w]; warpCnt[w] = tot; tot += t; }
+            chunkBase = tot ? (int)atomicAdd(cc, (uint32_t)tot) : 0;
+        }
+        __syncthreads();
+        if (sel) {
+            const uint32_t pos = (uint32_t)chunkBase + warpCnt[warp] + __popc(ball & ((1u << lane) - 1));
+            if (pos < (uint32_t)g.candCap) {
+                const uint32_t X = tx0 + 3 + (e & 0xff) - g.minB, Y = iniY + 3 + ((e >> 8) & 0xff) - g.minB;
+                out[pos] = X | (Y << 12) | ((((e >> 16) & 0xff) - 1) << 24);
+            } else {
+                *errFlag = CSLAM_E_CAPACITY;
+            }
+        }
+        __syncthreads();
     }
 }
 
@@ -941,7 +991,7 @@ static int launch_extract(cslam_frontend* fe, int batch, cslam_keypoint* d_kps, 
         const LevelGeom& g = fe->L.g[l];
         dim3 grid(cdiv(g.nColsEff, CG), g.nRowsEff, batch);
         mark(fe, KIND_FAST);
-        k_fast<<<grid, 256, 0, fe->stream>>>(fe->L.img[l], g, fe->orb.ini_th_fast, fe->orb.min_th_fast, fe->L.cand[l], fe->d_candCount + l, nl, fe->d_err);
+        k_fast<<<grid, 256, 0, fe->stream>>>(fe->L.img[l], g, fe->orb.ini_th_fast, fe->orb.min_th_fast, fe->L.cand[l], fe->d_candCount + l, nl, fe->d_err, nullptr);
     }
     CSLAM_CUDA(cudaGetLastError());
     DistributeArgs da;

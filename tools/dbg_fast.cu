@@ -19,7 +19,7 @@ int main() {
     cudaMalloc(&d_img, img.size()); cudaMemcpy(d_img, img.data(), img.size(), cudaMemcpyHostToDevice);
     cudaMalloc(&d_cand, 4 * 100000); cudaMalloc(&d_cnt, 4); cudaMemset(d_cnt, 0, 4); cudaMalloc(&d_err, 4); cudaMemset(d_err, 0, 4);
     dim3 grid(cdiv(g.nColsEff, CG), g.nRowsEff, 1);
-    k_fast<<<grid, 256>>>(d_img, g, 20, 7, d_cand, d_cnt, 1, d_err);
+    k_fast<<<grid, 256>>>(d_img, g, 20, 7, d_cand, d_cnt, 1, d_err, nullptr);
     cudaError_t e = cudaDeviceSynchronize();
     uint32_t n; cudaMemcpy(&n, d_cnt, 4, cudaMemcpyDeviceToHost);
     printf("sync %s, n=%u wCell=%d ncols=%d\n", cudaGetErrorString(e), n, g.wCell, g.nColsEff);
