@@ -51,6 +51,7 @@ struct DevLevels {
     const uint32_t* xab[MAX_LEVELS];   // a0 | a1<<16
     const uint16_t* yofs[MAX_LEVELS];
     const uint32_t* yab[MAX_LEVELS];
+    const uint8_t* skip[MAX_LEVELS];   // per k_fast CTA: 1 = tile provably all-zero when level 0 came from k_warp (black corner tiles)
     int nlevels;
 };
 
@@ -159,6 +160,10 @@ __device__ __forceinline__ uint32_t arc_score_x2(const uint32_t (&R)[16], uint32
     return __vmaxu2(t1, t2);
 }
 
+// q = i / d for 0 <= i < 65536/..: d-uniform fast division (tile loops have i < 8192, d <= 64)
+__device__ __forceinline__ int fdiv_small(int i, uint32_t magic) { return (int)(((uint32_t)i * magic) >> 20); }
+__device__ __forceinline__ uint32_t fdiv_magic(int d) { return ((1u << 20) + d - 1) / d; }
+
 // Layout of one CTA: CG cells of one cell row. Phases:
 //  A  branch-free exact arc score of every detection pixel (4 pixels per work item) -> S (u8, 0 where s <= minTh)
 //  B  3x3 NMS at minTh inside each cell -> shared list; a keypoint at iniTh is exactly an NMS survivor with s > iniTh
@@ -188,15 +193,26 @@ __global__ void __launch_bounds__(256) k_fast(const uint8_t* __restrict__ img, L
     if (tid == 0) { anyNonZero = 0; nK = 0; }
     __syncthreads();
     uint32_t acc = 0;
-    for (int r = warp; r < nrows; r += 8) {
-        const uint32_t* src = reinterpret_cast<const uint32_t*>(I + (size_t)(iniY + r) * g.pitch + a0);
-        uint32_t* dst = reinterpret_cast<uint32_t*>(tile + r * FAST_TS);
-        for (int wd = lane; wd < nwords; wd += 32) { const uint32_t v = __ldg(src + wd); dst[wd] = v; acc |= v; }
+    {
+        const uint32_t mg = fdiv_magic(nwords);
+        const uint8_t* base = I + (size_t)iniY * g.pitch + a0;
+        for (int i = tid; i < nwords * nrows; i += 256) {
+            const int r = fdiv_small(i, mg), wd = i - r * nwords;
+            const uint32_t v = __ldg(reinterpret_cast<const uint32_t*>(base + (size_t)r * g.pitch) + wd);
+            reinterpret_cast<uint32_t*>(tile + r * FAST_TS)[wd] = v;
+            acc |= v;
+        }
     }
     if (acc) anyNonZero = 1;
     const int nx = tx1 - tx0 - 6, ny = nrows - 6;   // detection area
     const int xoff = tx0 - a0 + 3;                   // tile column of detection x = 0
-    for (int i = tid; i < (ny + 2) * (FAST_TS / 4); i += 256) reinterpret_cast<uint32_t*>(S)[i] = 0;
+    const int w0 = xoff >> 2, w1 = (xoff + nx + 3) >> 2, nw = w1 - w0;   // S/tile words covering the detection columns
+    // S must read 0 around the scored area: rows 0 and ny+1, and the words left/right of [w0,w1) in every row
+    for (int i = tid; i < 2 * (FAST_TS / 4); i += 256) reinterpret_cast<uint32_t*>(S + (i >= FAST_TS / 4 ? (ny + 1) * FAST_TS : 0))[i % (FAST_TS / 4)] = 0;
+    for (int i = tid; i < 2 * ny; i += 256) {
+        const int r = (i >> 1) + 1, wsel = (i & 1) ? w1 : w0 - 1;
+        if (wsel >= 0 && wsel < FAST_TS / 4) reinterpret_cast<uint32_t*>(S + r * FAST_TS)[wsel] = 0;
+    }
     for (int x = tid; x < nx; x += 256) {
         const int c = x / g.wCell, xl = x - c * g.wCell;
         cellInfo[x] = (uint8_t)(c | (xl == 0 ? 0x40 : 0) | ((xl == g.wCell - 1 || x == nx - 1) ? 0x80 : 0));
@@ -204,11 +220,11 @@ __global__ void __launch_bounds__(256) k_fast(const uint8_t* __restrict__ img, L
     __syncthreads();
     if (!anyNonZero || nx <= 0 || ny <= 0) return;   // an all-zero tile has no corners at any threshold
     // ---- A
+    const uint32_t mgw = fdiv_magic(nw);
     {
-        const int w0 = xoff >> 2, w1 = (xoff + nx + 3) >> 2, nw = w1 - w0;
         const int nitems = nw * ny;
         for (int it = tid; it < nitems; it += 256) {
-            const int y = it / nw, wi = w0 + (it - y * nw);
+            const int y = fdiv_small(it, mgw), wi = w0 + (it - y * nw);
             const uint32_t* r0 = reinterpret_cast<const uint32_t*>(tile + y * FAST_TS) + wi;   // row y-3 relative to the centre row
             const int RS = FAST_TS / 4;
             uint32_t V[16];
@@ -260,10 +276,9 @@ __global__ void __launch_bounds__(256) k_fast(const uint8_t* __restrict__ img, L
     __syncthreads();
     // ---- B: NMS at minTh: keep s iff no same-cell neighbour n with s_n >= s (all stored scores are > minTh)
     {
-        const int w0 = xoff >> 2, w1 = (xoff + nx + 3) >> 2, nw = w1 - w0;
         const int nitems = nw * ny;
         for (int it = tid; it < nitems; it += 256) {
-            const int y = it / nw, wi = w0 + (it - y * nw);
+            const int y = fdiv_small(it, mgw), wi = w0 + (it - y * nw);
             uint32_t wv = reinterpret_cast<const uint32_t*>(S + (y + 1) * FAST_TS)[wi];
             while (wv) {
                 const int bq = (__ffs(wv) - 1) >> 3;
@@ -866,6 +881,46 @@ extern "C" int cslam_frontend_create(cslam_frontend** out, int device, const csl
                 (rc = dev_upload(fe, &fe->L.yab[l], ya))) return fail(rc);
         }
     }
+    // ---- static zero map: Z_0 = corner tiles of the canvas (never written by k_warp, zeroed at allocation); Z_l(x,y) = all four
+    // resize taps of (x,y) are in Z_{l-1}. A k_fast tile inside Z_l is all-zero, hence corner-free: its CTA exits at once.
+    {
+        std::vector<uint8_t> Z((size_t)fe->CW * fe->CH, 0), Zn;
+        for (int y = 0; y < fe->CH; y++)
+            for (int x = 0; x < fe->CW; x++) {
+                const int tc = x / fe->W, tr = y / fe->H;
+                Z[(size_t)y * fe->CW + x] = (tc != 1 && tr != 1) ? 1 : 0;
+            }
+        for (int l = 0; l < nl; l++) {
+            const LevelGeom& g = fe->L.g[l];
+            if (l > 0) {
+                const LevelGeom& sg = fe->L.g[l - 1];
+                std::vector<uint16_t> xo, yo; std::vector<uint32_t> xa, ya;
+                build_resize_tables(sg.w, g.w, xo, xa); build_resize_tables(sg.h, g.h, yo, ya);
+                Zn.assign((size_t)g.w * g.h, 0);
+                for (int y = 0; y < g.h; y++) {
+                    const int y0 = yo[y], y1 = std::min(y0 + 1, sg.h - 1);
+                    for (int x = 0; x < g.w; x++) {
+                        const int x0 = xo[x], x1 = std::min(x0 + 1, sg.w - 1);
+                        Zn[(size_t)y * g.w + x] = Z[(size_t)y0 * sg.w + x0] & Z[(size_t)y0 * sg.w + x1] & Z[(size_t)y1 * sg.w + x0] & Z[(size_t)y1 * sg.w + x1];
+                    }
+                }
+                Z.swap(Zn);
+            }
+            const int gx = cdiv(g.nColsEff, CG), gy = g.nRowsEff;
+            std::vector<uint8_t> sk((size_t)gx * gy, 0);
+            for (int cy = 0; cy < gy; cy++)
+                for (int cxg = 0; cxg < gx; cxg++) {
+                    const int iniY = g.minB + cy * g.hCell, maxY = std::min(iniY + g.hCell + 6, g.maxBY);
+                    const int ncell = std::min(CG, g.nColsEff - cxg * CG);
+                    const int tx0 = g.minB + cxg * CG * g.wCell, tx1 = std::min(tx0 + ncell * g.wCell + 6, g.maxBX);
+                    uint8_t all = 1;
+                    for (int y = iniY; y < maxY && all; y++)
+                        for (int x = tx0; x < tx1; x++) if (!Z[(size_t)y * g.w + x]) { all = 0; break; }
+                    sk[(size_t)cy * gx + cxg] = all;
+                }
+            if ((rc = dev_upload(fe, &fe->L.skip[l], sk))) return fail(rc);
+        }
+    }
     fe->M = round_up(std::max(maxQuota + 4, 16), 32);
     fe->keptCap = fe->M;
     fe->kpCap = orb->nfeatures + 3 * nl;
@@ -991,7 +1046,7 @@ static int launch_extract(cslam_frontend* fe, int batch, cslam_keypoint* d_kps, 
         const LevelGeom& g = fe->L.g[l];
         dim3 grid(cdiv(g.nColsEff, CG), g.nRowsEff, batch);
         mark(fe, KIND_FAST);
-        k_fast<<<grid, 256, 0, fe->stream>>>(fe->L.img[l], g, fe->orb.ini_th_fast, fe->orb.min_th_fast, fe->L.cand[l], fe->d_candCount + l, nl, fe->d_err, nullptr);
+        k_fast<<<grid, 256, 0, fe->stream>>>(fe->L.img[l], g, fe->orb.ini_th_fast, fe->orb.min_th_fast, fe->L.cand[l], fe->d_candCount + l, nl, fe->d_err, fe->cornersDirty ? nullptr : fe->L.skip[l]);
     }
     CSLAM_CUDA(cudaGetLastError());
     DistributeArgs da;
