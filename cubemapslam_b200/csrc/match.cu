@@ -1,0 +1,379 @@
+// 256-bit Hamming matching of libcubemap_b200.so, sm_100a.
+//
+// Reference (CPU): ORBMatcher::DescriptorDistance src/ORBMatcher.cpp:951-967 (SWAR popcount of 8 x 32-bit XOR),
+//   SearchByBoW(KeyFrame*,Frame&,...) :409-539, ComputeThreeMaxima :905-946, thresholds :42-45.
+// The all-pairs ("brute force") matcher of BASELINE config 3 has no reference function; DESIGN.md defines it as the
+// SearchByBoW acceptance rule + rotation histogram applied to the best/second-best column of every row of A.
+//
+// k_match_bruteforce  one CTA per pair; B is staged through shared memory in 128-descriptor tiles, every thread
+//                     owns one row of A (8 x u32 in registers), __popc per 32-bit lane; per-pair rotation histogram and
+//                     3-maxima filter in the same CTA. Bound by the integer/POPC issue rate, not by HBM (192 KB per pair).
+// k_search_by_bow     one CTA per pair; both FeatureVectors are rebuilt on the fly by an in-CTA bitonic sort of
+//                     (node, index); one warp walks the KF features of a node in order (the reference's "already
+//                     matched" skip makes that order matter), lanes scan the F features of the node.
+#include <cstring>
+#include <vector>
+#include "common.cuh"
+
+namespace cslam {
+
+static const int HISTO_BINS = 30;      // ceil(360 / HISTO_LENGTH), HISTO_LENGTH = 12
+static const int BF_THREADS = 256;
+static const int BF_TILE = 128;
+
+__device__ __forceinline__ int rot_bin(float a, float b) {
+    const float factor = 1.0f / 12.0f;
+    float rot = __fsub_rn(a, b);
+    if (rot < 0.0f) rot = __fadd_rn(rot, 360.0f);
+    int bin = (int)roundf(__fmul_rn(rot, factor));   // C round(): half away from zero
+    if (bin == HISTO_BINS) bin = 0;
+    return bin;
+}
+
+// ComputeThreeMaxima on bin counts (thread 0 only); keep[] = 1 for the bins that survive
+__device__ void three_maxima(const int* hist, int* keep) {
+    int max1 = 0, max2 = 0, max3 = 0, ind1 = -1, ind2 = -1, ind3 = -1;
+    for (int i = 0; i < HISTO_BINS; i++) {
+        const int s = hist[i];
+        if (s > max1) { max3 = max2; max2 = max1; max1 = s; ind3 = ind2; ind2 = ind1; ind1 = i; }
+        else if (s > max2) { max3 = max2; max2 = s; ind3 = ind2; ind2 = i; }
+        else if (s > max3) { max3 = s; ind3 = i; }
+    }
+    if ((float)max2 < __fmul_rn(0.1f, (float)max1)) { ind2 = -1; ind3 = -1; }
+    else if ((float)max3 < __fmul_rn(0.1f, (float)max1)) { ind3 = -1; }
+    for (int i = 0; i < HISTO_BINS; i++) keep[i] = (i == ind1 || i == ind2 || i == ind3);
+}
+
+__device__ __forceinline__ int hamming256(const uint32_t (&a)[8], const uint4 b0, const uint4 b1) {
+    return __popc(a[0] ^ b0.x) + __popc(a[1] ^ b0.y) + __popc(a[2] ^ b0.z) + __popc(a[3] ^ b0.w) +
+           __popc(a[4] ^ b1.x) + __popc(a[5] ^ b1.y) + __popc(a[6] ^ b1.z) + __popc(a[7] ^ b1.w);
+}
+
+__global__ void __launch_bounds__(BF_THREADS) k_match_bruteforce(const uint8_t* __restrict__ descA, const float* __restrict__ angA, int nA,
+                                                                 const uint8_t* __restrict__ descB, const float* __restrict__ angB, int nB, float nnratio,
+                                                                 int thLow, int checkOri, int32_t* __restrict__ match12, int32_t* __restrict__ dist12,
+                                                                 int32_t* __restrict__ second12, int32_t* __restrict__ nmatches) {
+    __shared__ __align__(16) uint4 sB[2 * BF_TILE];
+    __shared__ int hist[HISTO_BINS], keep[HISTO_BINS], total;
+    const int pair = blockIdx.x, tid = threadIdx.x;
+    const uint4* A4 = reinterpret_cast<const uint4*>(descA + (size_t)pair * nA * 32);
+    const uint4* B4 = reinterpret_cast<const uint4*>(descB + (size_t)pair * nB * 32);
+    const float* aA = angA + (size_t)pair * nA;
+    const float* aB = angB + (size_t)pair * nB;
+    int32_t* m12 = match12 + (size_t)pair * nA;
+    if (tid < HISTO_BINS) hist[tid] = 0;
+    if (tid == 0) total = 0;
+    __syncthreads();
+    for (int rbase = 0; rbase < nA; rbase += BF_THREADS) {
+        const int i = rbase + tid;
+        uint32_t a[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        if (i < nA) {
+            const uint4 a0 = __ldg(A4 + 2 * i), a1 = __ldg(A4 + 2 * i + 1);
+            a[0] = a0.x; a[1] = a0.y; a[2] = a0.z; a[3] = a0.w; a[4] = a1.x; a[5] = a1.y; a[6] = a1.z; a[7] = a1.w;
+        }
+        int best1 = 256, best2 = 256, bestIdx = -1;
+        for (int cb = 0; cb < nB; cb += BF_TILE) {
+            const int nt = min(BF_TILE, nB - cb);
+            __syncthreads();
+            for (int k = tid; k < 2 * nt; k += BF_THREADS) sB[k] = __ldg(B4 + 2 * cb + k);
+            __syncthreads();
+            if (i < nA) {
+#pragma unroll 4
+                for (int j = 0; j < nt; j++) {
+                    const int d = hamming256(a, sB[2 * j], sB[2 * j + 1]);
+                    if (d < best1) { best2 = best1; best1 = d; bestIdx = cb + j; }
+                    else if (d < best2) best2 = d;
+                }
+            }
+        }
+        if (i < nA) {
+            int m = -1;
+            if (bestIdx >= 0 && best1 <= thLow && (float)best1 < __fmul_rn(nnratio, (float)best2)) {
+                m = bestIdx;
+                if (checkOri) atomicAdd(&hist[rot_bin(aA[i], aB[bestIdx])], 1);
+                atomicAdd(&total, 1);
+            }
+            m12[i] = m;
+            if (dist12) dist12[(size_t)pair * nA + i] = best1;
+            if (second12) second12[(size_t)pair * nA + i] = best2;
+        }
+    }
+    __syncthreads();
+    if (checkOri) {
+        if (tid == 0) three_maxima(hist, keep);
+        __syncthreads();
+        for (int i = tid; i < nA; i += BF_THREADS) {
+            const int m = m12[i];
+            if (m >= 0 && !keep[rot_bin(aA[i], aB[m])]) { m12[i] = -1; atomicSub(&total, 1); }
+        }
+        __syncthreads();
+    }
+    if (tid == 0) nmatches[pair] = total;
+}
+
+// ------------------------------------------------------------------------------------------------- SearchByBoW
+static const int BOW_THREADS = 256;
+
+__device__ void bitonic_sort(uint32_t* key, int n2) {   // ascending, n2 power of two
+    for (int k = 2; k <= n2; k <<= 1)
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int t = threadIdx.x; t < n2; t += blockDim.x) {
+                const int ixj = t ^ j;
+                if (ixj > t) {
+                    const uint32_t a = key[t], b = key[ixj];
+                    const bool up = (t & k) == 0;
+                    if ((a > b) == up) { key[t] = b; key[ixj] = a; }
+                }
+            }
+            __syncthreads();
+        }
+}
+
+// keys: node << 12 | index (index < 4096, node < 2^20). Shared memory: keyKF[n2K], keyF[n2F], takenF[nF] bytes.
+__global__ void __launch_bounds__(BOW_THREADS) k_search_by_bow(const uint8_t* __restrict__ descKF, const float* __restrict__ angKF,
+                                                               const uint8_t* __restrict__ kfValid, const int32_t* __restrict__ nodeKF, int nKF,
+                                                               const uint8_t* __restrict__ descF, const float* __restrict__ angF,
+                                                               const int32_t* __restrict__ nodeF, int nF, int n2K, int n2F, float nnratio, int checkOri,
+                                                               int32_t* __restrict__ matchF, int32_t* __restrict__ nmatches) {
+    extern __shared__ __align__(16) uint8_t smem[];
+    uint32_t* keyKF = reinterpret_cast<uint32_t*>(smem);
+    uint32_t* keyF = keyKF + n2K;
+    int* mF = reinterpret_cast<int*>(keyF + n2F);   // match per F feature (KF index or -1), staged in shared memory
+    __shared__ int hist[HISTO_BINS], keep[HISTO_BINS], total;
+    const int pair = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = BOW_THREADS / 32;
+    const uint4* K4 = reinterpret_cast<const uint4*>(descKF + (size_t)pair * nKF * 32);
+    const uint4* F4 = reinterpret_cast<const uint4*>(descF + (size_t)pair * nF * 32);
+    const float* aK = angKF + (size_t)pair * nKF;
+    const float* aF = angF + (size_t)pair * nF;
+    const uint8_t* val = kfValid + (size_t)pair * nKF;
+    const int32_t* nK = nodeKF + (size_t)pair * nKF;
+    const int32_t* nFd = nodeF + (size_t)pair * nF;
+    for (int i = tid; i < n2K; i += BOW_THREADS) keyKF[i] = i < nKF ? ((uint32_t)nK[i] << 12) | (uint32_t)i : 0xffffffffu;
+    for (int i = tid; i < n2F; i += BOW_THREADS) keyF[i] = i < nF ? ((uint32_t)nFd[i] << 12) | (uint32_t)i : 0xffffffffu;
+    for (int i = tid; i < nF; i += BOW_THREADS) mF[i] = -1;
+    if (tid < HISTO_BINS) hist[tid] = 0;
+    if (tid == 0) total = 0;
+    __syncthreads();
+    bitonic_sort(keyKF, n2K);
+    bitonic_sort(keyF, n2F);
+    // one warp per KF node group: a group starts where the node id changes
+    for (int s = warp; s < nKF; s += nwarps) {
+        // warps take candidate group starts round-robin: position s is a start iff s==0 or node differs from s-1
+        // (cheap: every warp scans its own positions; groups are independent of each other)
+        const uint32_t node = keyKF[s] >> 12;
+        if (s > 0 && (keyKF[s - 1] >> 12) == node) continue;
+        // KF group [s, e)
+        int e = s + 1;
+        while (e < nKF && (keyKF[e] >> 12) == node) e++;
+        // F group by binary search of node << 12
+        int lo = 0, hi = nF;
+        const uint32_t target = node << 12;
+        while (lo < hi) { const int mid = (lo + hi) >> 1; if (keyF[mid] < target) lo = mid + 1; else hi = mid; }
+        const int fs = lo;
+        int fe = fs;
+        while (fe < nF && (keyF[fe] >> 12) == node) fe++;
+        if (fe == fs) continue;
+        for (int q = s; q < e; q++) {
+            const int iK = keyKF[q] & 0xfff;
+            if (!val[iK]) continue;
+            const uint4 k0 = __ldg(K4 + 2 * iK), k1 = __ldg(K4 + 2 * iK + 1);
+            const uint32_t a[8] = {k0.x, k0.y, k0.z, k0.w, k1.x, k1.y, k1.z, k1.w};
+            // lanes scan the F features of the node in list order; (best1, pos, best2) with first-position ties
+            int best1 = 256, best2 = 256, bpos = 0x7fffffff;
+            for (int p = fs + lane; p < fe; p += 32) {
+                const int iF = keyF[p] & 0xfff;
+                if (mF[iF] >= 0) continue;
+                const int d = hamming256(a, __ldg(F4 + 2 * iF), __ldg(F4 + 2 * iF + 1));
+                if (d < best1) { best2 = best1; best1 = d; bpos = p; }
+                else if (d < best2) best2 = d;
+            }
+#pragma unroll
+            for (int o = 16; o; o >>= 1) {
+                const int ob1 = __shfl_xor_sync(0xffffffffu, best1, o), ob2 = __shfl_xor_sync(0xffffffffu, best2, o), op = __shfl_xor_sync(0xffffffffu, bpos, o);
+                // merge two partial scans: the winner is the smaller distance, ties go to the earlier list position
+                const bool otherWins = ob1 < best1 || (ob1 == best1 && op < bpos);
+                if (otherWins) { best2 = min(best1, ob2); best1 = ob1; bpos = op; }
+                else best2 = min(best2, ob1);
+            }
+            if (best1 <= 50 && (float)best1 < __fmul_rn(nnratio, (float)best2)) {
+                const int iF = keyF[bpos] & 0xfff;
+                if (lane == 0) {
+                    mF[iF] = iK;
+                    if (checkOri) atomicAdd(&hist[rot_bin(aK[iK], aF[iF])], 1);
+                    atomicAdd(&total, 1);
+                }
+            }
+            __syncwarp();
+        }
+    }
+    __syncthreads();
+    if (checkOri) {
+        if (tid == 0) three_maxima(hist, keep);
+        __syncthreads();
+        for (int j = tid; j < nF; j += BOW_THREADS) {
+            const int m = mF[j];
+            if (m >= 0 && !keep[rot_bin(aK[m], aF[j])]) { mF[j] = -1; atomicSub(&total, 1); }
+        }
+        __syncthreads();
+    }
+    int32_t* out = matchF + (size_t)pair * nF;
+    for (int j = tid; j < nF; j += BOW_THREADS) out[j] = mF[j];
+    if (tid == 0) nmatches[pair] = total;
+}
+
+__global__ void k_hamming(const uint8_t* __restrict__ a, const uint8_t* __restrict__ b, int n, int32_t* __restrict__ dist) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint4* A4 = reinterpret_cast<const uint4*>(a) + 2 * (size_t)i;
+    const uint4* B4 = reinterpret_cast<const uint4*>(b) + 2 * (size_t)i;
+    const uint4 a0 = __ldg(A4), a1 = __ldg(A4 + 1);
+    const uint32_t av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+    dist[i] = hamming256(av, __ldg(B4), __ldg(B4 + 1));
+}
+
+}  // namespace cslam
+
+using namespace cslam;
+
+struct cslam_matcher {
+    int device = 0, maxPairs = 0, maxFeat = 0;
+    cudaStream_t stream = nullptr;
+    uint8_t *dA = nullptr, *dB = nullptr, *dValid = nullptr;
+    float *aA = nullptr, *aB = nullptr;
+    int32_t *nodeA = nullptr, *nodeB = nullptr, *dMatch = nullptr, *dDist = nullptr, *dSecond = nullptr, *dN = nullptr;
+    int64_t launches = 0;
+};
+
+extern "C" int cslam_matcher_create(cslam_matcher** out, int device, int max_pairs, int max_features) {
+    if (!out || max_pairs <= 0 || max_features <= 0 || max_features > 4096) { set_error("cslam_matcher_create: bad argument (max_features <= 4096)"); return CSLAM_E_BADARG; }
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) { set_error("no CUDA device (this library has no CPU fallback)"); return CSLAM_E_NODEVICE; }
+    if (device < 0 || device >= ndev) { set_error("device %d out of range", device); return CSLAM_E_BADARG; }
+    CSLAM_CUDA(cudaSetDevice(device));
+    cslam_matcher* m = new cslam_matcher;
+    m->device = device; m->maxPairs = max_pairs; m->maxFeat = max_features;
+    const size_t nf = (size_t)max_pairs * max_features;
+    if (cudaStreamCreateWithFlags(&m->stream, cudaStreamNonBlocking) != cudaSuccess || cudaMalloc(&m->dA, nf * 32) != cudaSuccess || cudaMalloc(&m->dB, nf * 32) != cudaSuccess ||
+        cudaMalloc(&m->dValid, nf) != cudaSuccess || cudaMalloc(&m->aA, nf * 4) != cudaSuccess || cudaMalloc(&m->aB, nf * 4) != cudaSuccess ||
+        cudaMalloc(&m->nodeA, nf * 4) != cudaSuccess || cudaMalloc(&m->nodeB, nf * 4) != cudaSuccess || cudaMalloc(&m->dMatch, nf * 4) != cudaSuccess ||
+        cudaMalloc(&m->dDist, nf * 4) != cudaSuccess || cudaMalloc(&m->dSecond, nf * 4) != cudaSuccess || cudaMalloc(&m->dN, (size_t)max_pairs * 4) != cudaSuccess) {
+        set_error("matcher: device allocation failed");
+        cslam_matcher_destroy(m);
+        return CSLAM_E_CUDA;
+    }
+    cudaFuncSetAttribute(k_search_by_bow, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+    *out = m;
+    return CSLAM_OK;
+}
+
+extern "C" void cslam_matcher_destroy(cslam_matcher* m) {
+    if (!m) return;
+    cudaSetDevice(m->device);
+    if (m->stream) { cudaStreamSynchronize(m->stream); cudaStreamDestroy(m->stream); }
+    void* ptrs[] = {m->dA, m->dB, m->dValid, m->aA, m->aB, m->nodeA, m->nodeB, m->dMatch, m->dDist, m->dSecond, m->dN};
+    for (void* p : ptrs) if (p) cudaFree(p);
+    delete m;
+}
+extern "C" void* cslam_matcher_stream(const cslam_matcher* m) { return m ? (void*)m->stream : nullptr; }
+extern "C" int64_t cslam_matcher_launches(const cslam_matcher* m) { return m ? m->launches : 0; }
+extern "C" int cslam_matcher_sync(cslam_matcher* m) {
+    if (!m) return CSLAM_E_BADARG;
+    CSLAM_CUDA(cudaSetDevice(m->device));
+    CSLAM_CUDA(cudaStreamSynchronize(m->stream));
+    return CSLAM_OK;
+}
+
+static int check_sizes(cslam_matcher* m, int nA, int nB, int npairs) {
+    if (!m || nA < 0 || nB < 0 || npairs <= 0 || npairs > m->maxPairs || nA > m->maxFeat || nB > m->maxFeat) {
+        set_error("matcher: sizes out of range (pairs %d/%d, features %d,%d/%d)", npairs, m ? m->maxPairs : 0, nA, nB, m ? m->maxFeat : 0);
+        return CSLAM_E_BADARG;
+    }
+    CSLAM_CUDA(cudaSetDevice(m->device));
+    return 0;
+}
+
+extern "C" int cslam_match_bruteforce_dev(cslam_matcher* m, const uint8_t* descA, const float* angA, int nA, const uint8_t* descB, const float* angB, int nB,
+                                          int npairs, float nnratio, int th_low, int check_ori, int32_t* match12, int32_t* dist12, int32_t* second12,
+                                          int32_t* nmatches) {
+    int rc = check_sizes(m, nA, nB, npairs);
+    if (rc) return rc;
+    if (nA == 0) { CSLAM_CUDA(cudaMemsetAsync(nmatches, 0, (size_t)npairs * 4, m->stream)); return CSLAM_OK; }
+    k_match_bruteforce<<<npairs, BF_THREADS, 0, m->stream>>>(descA, angA, nA, descB, angB, nB, nnratio, th_low, check_ori, match12, dist12, second12, nmatches);
+    m->launches++;
+    CSLAM_CUDA(cudaGetLastError());
+    return CSLAM_OK;
+}
+
+extern "C" int cslam_match_bruteforce(cslam_matcher* m, const uint8_t* descA, const float* angA, int nA, const uint8_t* descB, const float* angB, int nB, int npairs,
+                                      float nnratio, int th_low, int check_ori, int32_t* match12, int32_t* dist12, int32_t* second12, int32_t* nmatches) {
+    int rc = check_sizes(m, nA, nB, npairs);
+    if (rc) return rc;
+    const size_t na = (size_t)npairs * nA, nb = (size_t)npairs * nB;
+    if (na) { CSLAM_CUDA(cudaMemcpyAsync(m->dA, descA, na * 32, cudaMemcpyHostToDevice, m->stream)); CSLAM_CUDA(cudaMemcpyAsync(m->aA, angA, na * 4, cudaMemcpyHostToDevice, m->stream)); }
+    if (nb) { CSLAM_CUDA(cudaMemcpyAsync(m->dB, descB, nb * 32, cudaMemcpyHostToDevice, m->stream)); CSLAM_CUDA(cudaMemcpyAsync(m->aB, angB, nb * 4, cudaMemcpyHostToDevice, m->stream)); }
+    rc = cslam_match_bruteforce_dev(m, m->dA, m->aA, nA, m->dB, m->aB, nB, npairs, nnratio, th_low, check_ori, m->dMatch, m->dDist, m->dSecond, m->dN);
+    if (rc) return rc;
+    if (na) {
+        CSLAM_CUDA(cudaMemcpyAsync(match12, m->dMatch, na * 4, cudaMemcpyDeviceToHost, m->stream));
+        if (dist12) CSLAM_CUDA(cudaMemcpyAsync(dist12, m->dDist, na * 4, cudaMemcpyDeviceToHost, m->stream));
+        if (second12) CSLAM_CUDA(cudaMemcpyAsync(second12, m->dSecond, na * 4, cudaMemcpyDeviceToHost, m->stream));
+    }
+    CSLAM_CUDA(cudaMemcpyAsync(nmatches, m->dN, (size_t)npairs * 4, cudaMemcpyDeviceToHost, m->stream));
+    CSLAM_CUDA(cudaStreamSynchronize(m->stream));
+    return CSLAM_OK;
+}
+
+static int pow2_at_least(int n) { int p = 1; while (p < n) p <<= 1; return p; }
+
+extern "C" int cslam_search_by_bow_dev(cslam_matcher* m, const uint8_t* descKF, const float* angKF, const uint8_t* kf_valid, const int32_t* node_kf, int nKF,
+                                       const uint8_t* descF, const float* angF, const int32_t* node_f, int nF, int npairs, float nnratio, int check_ori,
+                                       int32_t* match_f, int32_t* nmatches) {
+    int rc = check_sizes(m, nKF, nF, npairs);
+    if (rc) return rc;
+    if (nF == 0 || nKF == 0) {
+        CSLAM_CUDA(cudaMemsetAsync(nmatches, 0, (size_t)npairs * 4, m->stream));
+        if (nF) CSLAM_CUDA(cudaMemsetAsync(match_f, 0xff, (size_t)npairs * nF * 4, m->stream));
+        return CSLAM_OK;
+    }
+    const int n2K = pow2_at_least(nKF), n2F = pow2_at_least(nF);
+    const size_t smem = (size_t)(n2K + n2F + nF) * 4;
+    k_search_by_bow<<<npairs, BOW_THREADS, smem, m->stream>>>(descKF, angKF, kf_valid, node_kf, nKF, descF, angF, node_f, nF, n2K, n2F, nnratio, check_ori, match_f, nmatches);
+    m->launches++;
+    CSLAM_CUDA(cudaGetLastError());
+    return CSLAM_OK;
+}
+
+extern "C" int cslam_search_by_bow(cslam_matcher* m, const uint8_t* descKF, const float* angKF, const uint8_t* kf_valid, const int32_t* node_kf, int nKF,
+                                   const uint8_t* descF, const float* angF, const int32_t* node_f, int nF, int npairs, float nnratio, int check_ori, int32_t* match_f,
+                                   int32_t* nmatches) {
+    int rc = check_sizes(m, nKF, nF, npairs);
+    if (rc) return rc;
+    const size_t nk = (size_t)npairs * nKF, nf = (size_t)npairs * nF;
+    if (nk) {
+        CSLAM_CUDA(cudaMemcpyAsync(m->dA, descKF, nk * 32, cudaMemcpyHostToDevice, m->stream)); CSLAM_CUDA(cudaMemcpyAsync(m->aA, angKF, nk * 4, cudaMemcpyHostToDevice, m->stream));
+        CSLAM_CUDA(cudaMemcpyAsync(m->dValid, kf_valid, nk, cudaMemcpyHostToDevice, m->stream)); CSLAM_CUDA(cudaMemcpyAsync(m->nodeA, node_kf, nk * 4, cudaMemcpyHostToDevice, m->stream));
+    }
+    if (nf) {
+        CSLAM_CUDA(cudaMemcpyAsync(m->dB, descF, nf * 32, cudaMemcpyHostToDevice, m->stream)); CSLAM_CUDA(cudaMemcpyAsync(m->aB, angF, nf * 4, cudaMemcpyHostToDevice, m->stream));
+        CSLAM_CUDA(cudaMemcpyAsync(m->nodeB, node_f, nf * 4, cudaMemcpyHostToDevice, m->stream));
+    }
+    rc = cslam_search_by_bow_dev(m, m->dA, m->aA, m->dValid, m->nodeA, nKF, m->dB, m->aB, m->nodeB, nF, npairs, nnratio, check_ori, m->dMatch, m->dN);
+    if (rc) return rc;
+    if (nf) CSLAM_CUDA(cudaMemcpyAsync(match_f, m->dMatch, nf * 4, cudaMemcpyDeviceToHost, m->stream));
+    CSLAM_CUDA(cudaMemcpyAsync(nmatches, m->dN, (size_t)npairs * 4, cudaMemcpyDeviceToHost, m->stream));
+    CSLAM_CUDA(cudaStreamSynchronize(m->stream));
+    return CSLAM_OK;
+}
+
+extern "C" int cslam_hamming(cslam_matcher* m, const uint8_t* a, const uint8_t* b, int n, int32_t* dist) {
+    if (!m || n < 0 || (size_t)n > (size_t)m->maxPairs * m->maxFeat) { set_error("cslam_hamming: n out of range"); return CSLAM_E_BADARG; }
+    if (n == 0) return CSLAM_OK;
+    CSLAM_CUDA(cudaSetDevice(m->device));
+    CSLAM_CUDA(cudaMemcpyAsync(m->dA, a, (size_t)n * 32, cudaMemcpyHostToDevice, m->stream));
+    CSLAM_CUDA(cudaMemcpyAsync(m->dB, b, (size_t)n * 32, cudaMemcpyHostToDevice, m->stream));
+    k_hamming<<<cdiv(n, 256), 256, 0, m->stream>>>(m->dA, m->dB, n, m->dDist);
+    m->launches++;
+    CSLAM_CUDA(cudaMemcpyAsync(dist, m->dDist, (size_t)n * 4, cudaMemcpyDeviceToHost, m->stream));
+    CSLAM_CUDA(cudaStreamSynchronize(m->stream));
+    return CSLAM_OK;
+}
