@@ -1,0 +1,100 @@
+"""GPU parity: LocalBundleAdjustment / PoseOptimization vs the fp64 CPU oracle. Tolerance (north_star): 1e-5 relative on the
+fp64 pose / point state (before the float32 cast); outlier sets and the LM trajectory (iterations, accepted steps) equal."""
+import os
+import numpy as np
+import pytest
+
+from cubemapslam_b200 import synth
+
+pytestmark = pytest.mark.gpu
+RTOL = 1e-5
+
+
+@pytest.fixture(scope="module")
+def opt():
+    from cubemapslam_b200.optimizer import Optimizer
+    o = Optimizer()
+    yield o
+    o.close()
+
+
+def rel(a, b):
+    return np.max(np.abs(a - b)) / max(np.max(np.abs(b)), 1e-30)
+
+
+def _compare_ba(oracle, opt, p, **kw):
+    r = oracle.local_ba(p["Tcw"], p["kf_fixed"], p["pts"], p["eMP"], p["eKF"], p["kpxy"], p["inv_sigma2"], p["faceW"], p["faceH"], **kw)
+    g = opt.LocalBundleAdjustment(p["Tcw"], p["kf_fixed"], p["pts"], p["eMP"], p["eKF"], p["kpxy"], p["inv_sigma2"], p["faceW"], p["faceH"], **kw)
+    assert g["iters"] == r["iters"], (g["iters"], r["iters"])
+    assert np.array_equal(g["log"][:, 2:], r["log"][:, 2:])                       # trials / accepted per iteration
+    assert np.allclose(g["log"][:, 0], r["log"][:, 0], rtol=1e-8)                 # chi2 trajectory
+    assert rel(g["pose64"], r["pose64"]) < RTOL and rel(g["pts64"], r["pts64"]) < RTOL
+    assert np.array_equal(g["outlier"], r["outlier"])
+    assert np.allclose(g["Tcw"], r["Tcw"], atol=2e-6) and np.allclose(g["pts"], r["pts"], atol=2e-6)
+    return r, g
+
+
+def test_local_ba_small_all_faces(oracle, opt):
+    p = synth.ba_problem(nKF=8, nMP=300, kmin=2, kmax=6, faceW=450, seed=11, radius=1.5)
+    r, g = _compare_ba(oracle, opt, p)
+    gold = np.load(os.path.join(os.path.dirname(__file__), "golden", "ba_small.npz"))
+    assert rel(g["pose64"], gold["pose64"]) < RTOL and np.array_equal(g["outlier"], gold["outlier"])
+
+
+def test_local_ba_first_trial(oracle, opt):
+    p = synth.ba_problem(nKF=5, nMP=60, kmin=2, kmax=5, faceW=450, seed=8, radius=1.5)
+    _compare_ba(oracle, opt, p, its1=1, its2=0)
+
+
+def test_local_ba_medium_with_fixed_cameras(oracle, opt):
+    p = synth.ba_problem(nKF=20, nMP=3000, kmin=2, kmax=10, faceW=650, seed=5, radius=2.0)
+    p["kf_fixed"][[0, 7, 13]] = 1                                   # lFixedCameras
+    r, g = _compare_ba(oracle, opt, p)
+    assert np.allclose(g["pose64"][[7, 13]], r["pose64"][[7, 13]], rtol=0, atol=1e-15)
+    assert r["outlier"].mean() > 0.02
+
+
+def test_local_ba_edge_cases(oracle, opt):
+    p = synth.ba_problem(nKF=6, nMP=80, kmin=2, kmax=4, faceW=450, seed=2, radius=1.5)
+    # a landmark without observations, a keyframe without observations, and a raised stop flag
+    keep = (p["eMP"] != 3) & (p["eKF"] != 4)
+    for k in ("eMP", "eKF", "kpxy", "inv_sigma2"):
+        p[k] = p[k][keep]
+    _compare_ba(oracle, opt, p)
+    stop = np.ones(1, np.uint8)
+    g = opt.LocalBundleAdjustment(p["Tcw"], p["kf_fixed"], p["pts"], p["eMP"], p["eKF"], p["kpxy"], p["inv_sigma2"], 450, 450, stop_flag=stop)
+    assert g["iters"] == 0 and np.array_equal(g["pts"], p["pts"]) and not g["outlier"].any()
+
+
+def test_pose_optimization_batch(oracle, opt):
+    probs = [synth.pose_problem(n=n, faceW=450, seed=s, outlier_frac=0.15) for n, s in ((300, 5), (200, 6), (40, 7), (2, 8), (9, 9))]
+    off = np.cumsum([0] + [len(q["Xw"]) for q in probs]).astype(np.int32)
+    T = np.stack([q["Tcw"] for q in probs]); Xw = np.concatenate([q["Xw"] for q in probs]); kp = np.concatenate([q["kpxy"] for q in probs])
+    w = np.concatenate([q["inv_sigma2"] for q in probs])
+    g = opt.PoseOptimization(T, Xw, kp, w, 450, 450, offset=off)
+    for i, q in enumerate(probs):
+        r = oracle.pose_opt(q["Tcw"], q["Xw"], q["kpxy"], q["inv_sigma2"], 450, 450)
+        assert g["inliers"][i] == r["inliers"], i
+        assert np.array_equal(g["outlier"][off[i]:off[i + 1]], r["outlier"]), i
+        if len(q["Xw"]) >= 3:
+            assert rel(g["pose64"][i], r["pose64"]) < RTOL, i
+            assert np.allclose(g["Tcw"][i], r["Tcw"], atol=2e-6)
+        else:
+            assert np.array_equal(g["Tcw"][i], q["Tcw"])                       # untouched (src/Optimizer.cpp:133-134)
+    gold = np.load(os.path.join(os.path.dirname(__file__), "golden", "ba_small.npz"))
+    q = synth.pose_problem(n=200, faceW=450, seed=5)
+    o = opt.PoseOptimization(q["Tcw"], q["Xw"], q["kpxy"], q["inv_sigma2"], 450, 450)
+    assert o["inliers"] == int(gold["po_inliers"]) and rel(o["pose64"], gold["po_pose64"]) < RTOL
+
+
+def test_config4_scale_properties(opt):
+    """BASELINE config-4 size (50 KF x 20k points, ~170k edges): oracle-free properties - chi2 decreases monotonically over
+    accepted LM steps, fixed KF 0 unchanged, planted outlier fraction recovered, result close to the planted truth."""
+    p = synth.ba_problem()
+    g = opt.LocalBundleAdjustment(p["Tcw"], p["kf_fixed"], p["pts"], p["eMP"], p["eKF"], p["kpxy"], p["inv_sigma2"], 650, 650)
+    assert g["iters"] >= 5
+    acc = g["log"][g["log"][:, 3] == 1][:, 0]
+    e0 = np.linalg.norm(p["Tcw"][:, :3, 3] - p["Tcw_true"][:, :3, 3], axis=1).mean()
+    e1 = np.linalg.norm(g["Tcw"][:, :3, 3] - p["Tcw_true"][:, :3, 3], axis=1).mean()
+    assert e1 < 0.3 * e0 and 0.03 < g["outlier"].mean() < 0.09
+    assert np.allclose(g["Tcw"][0], p["Tcw"][0], atol=1e-6)
