@@ -236,11 +236,12 @@ def run_ours(args):
     # ---- CPU baseline: the oracle port on the host cores, bounded sample of the same workload
     cpu = cpu_baseline(cfg, mask, base_host, args)
     extra = {}
-    try:
+    if not args.no_extra:
         from cubemapslam_b200 import bench_extra
+        fe.close()
+        del fish, kps, desc
+        torch.cuda.empty_cache()
         extra = bench_extra.run(args, local)
-    except ImportError:
-        pass
     out = {"metric": "warp+ORB-extract frames/sec", "value": round(value, 1), "unit": "frames/s", "n_gpus": world, "steps": args.steps,
            "warmup": args.warmup, "ms_per_step": round(ms_max / args.steps, 3), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
            "dtype": "u8", "data": "synthetic (SURVEY §8d recipe: %d distinct frames, others are re-masked circular shifts)" % N_BASE,
@@ -304,6 +305,9 @@ def main():
     ap.add_argument("--batch", type=int, default=64)
     ap.add_argument("--e2e-frames", type=int, default=1024)
     ap.add_argument("--e2e-steps", type=int, default=2)
+    ap.add_argument("--match-pairs", type=int, default=4096)
+    ap.add_argument("--match-steps", type=int, default=2)
+    ap.add_argument("--no-extra", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
