@@ -787,6 +787,7 @@ static void host_cubemap_to_fisheye(const cslam_cam_params& cp, double up, doubl
 template <class T>
 static int dev_alloc(cslam_frontend* fe, T** p, size_t count, bool zero = true) {
     void* q = nullptr;
+    if (count == 0) count = 1;
     CSLAM_CUDA(cudaMalloc(&q, count * sizeof(T)));
     if (zero) CSLAM_CUDA(cudaMemset(q, 0, count * sizeof(T)));
     fe->owned.push_back(q);
@@ -929,7 +930,8 @@ extern "C" int cslam_frontend_create(cslam_frontend** out, int device, const csl
     if (fe->distributeSmem > 200 * 1024) { set_error("nfeatures too large for the shared-memory quadtree (%zu B)", fe->distributeSmem); return fail(CSLAM_E_BADARG); }
     if (cudaFuncSetAttribute(k_distribute, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fe->distributeSmem) != cudaSuccess) { set_error("cudaFuncSetAttribute failed"); return fail(CSLAM_E_CUDA); }
     // ---- System::CreateUndistortRectifyMap (src/System.cpp:301-324) on the host, then quantised like cv::remap does
-    {
+    // (skipped when no fisheye geometry is given: extraction-only front end, e.g. the ORBextractor facade)
+    if (cam->Iw > 0 && cam->Ih > 0) {
         const int CW = fe->CW, CH = fe->CH, W = fe->W;
         fe->map1.assign((size_t)CW * CH, 0.f); fe->map2.assign((size_t)CW * CH, 0.f);
         for (int y = 0; y < CH; y++)
@@ -1020,6 +1022,7 @@ extern "C" int cslam_frontend_sync(cslam_frontend* fe) {
 
 static int launch_warp(cslam_frontend* fe, const uint8_t* d_fisheye, int batch) {
     const int FPT = 4;
+    if (!fe->d_map) { set_error("this front end was created without fisheye geometry (Iw/Ih = 0): no warp"); return CSLAM_E_BADARG; }
     if (fe->cornersDirty) {   // the warp never writes the 4 corner tiles; they must read as the reference's zeroed canvas
         CSLAM_CUDA(cudaMemsetAsync(fe->L.img[0], 0, (size_t)fe->maxBatch * fe->L.g[0].pitch * fe->CH, fe->stream));
         fe->cornersDirty = false;
