@@ -237,7 +237,7 @@ def run_ours(args):
     cpu = cpu_baseline(cfg, mask, base_host, args)
     extra = {}
     if not args.no_extra:
-        from cubemapslam_b200 import bench_extra
+        import bench_extra
         fe.close()
         del fish, kps, desc
         torch.cuda.empty_cache()

@@ -5,11 +5,11 @@ import time
 
 import numpy as np
 
-from . import synth
+from cubemapslam_b200 import synth
 
 
 def _match_leg(torch, dev, args, local):
-    from .matcher import ORBMatcher
+    from cubemapslam_b200.matcher import ORBMatcher
     P, n = args.match_pairs, 2000
     nb = 16
     base = [synth.descriptor_pair(p, n=n) for p in range(nb)]
@@ -69,7 +69,7 @@ def _match_leg(torch, dev, args, local):
 
 
 def _ba_leg(args, local):
-    from .optimizer import Optimizer
+    from cubemapslam_b200.optimizer import Optimizer
     import oracle as orc
     p = synth.ba_problem()   # config 4: 50 KF x 20k points, ~170k edges
     o = Optimizer(device=local)
