@@ -179,7 +179,10 @@ def run_ours(args):
     ef = min(args.e2e_frames, frames)
     h_in = torch.empty((ef, fish.shape[1], fish.shape[2]), dtype=torch.uint8).pin_memory()
     h_in.copy_(fish[:ef].cpu())
-    h_kps = np.empty((B, kp_cap), _capi.KP_DTYPE); h_desc = np.empty((B, kp_cap, 32), np.uint8); h_n = np.empty(B, np.int32)
+    # page-locked result buffers: the library DMAs straight into caller memory when it is pinned
+    t_kps = torch.empty((B, kp_cap, 28), dtype=torch.uint8).pin_memory(); t_desc = torch.empty((B, kp_cap, 32), dtype=torch.uint8).pin_memory()
+    t_n = torch.empty((B,), dtype=torch.int32).pin_memory()
+    h_kps = t_kps.numpy(); h_desc = t_desc.numpy(); h_n = t_n.numpy()
     h_np = h_in.numpy()
 
     def e2e_pass():

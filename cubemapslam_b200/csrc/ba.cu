@@ -526,7 +526,9 @@ struct cslam_optimizer {
     cudaStream_t stream = nullptr;
     nccl_comm_t comm = nullptr; int rank = 0, nranks = 1;
     int64_t launches = 0;
-    std::vector<void*> pool;   // device allocations of the current problem
+    // device arena: chunks are kept across calls (cudaMalloc/cudaFree per BA call cost more than the solve itself)
+    struct Chunk { char* p; size_t size, used; };
+    std::vector<Chunk> chunks;
     double* h_scal = nullptr;  // pinned
 };
 
@@ -546,12 +548,13 @@ extern "C" int cslam_optimizer_create(cslam_optimizer** out, int device) {
     *out = o;
     return CSLAM_OK;
 }
-static void free_pool(cslam_optimizer* o) { for (void* p : o->pool) cudaFree(p); o->pool.clear(); }
+static void free_pool(cslam_optimizer* o) { for (auto& c : o->chunks) c.used = 0; }
+static void release_pool(cslam_optimizer* o) { for (auto& c : o->chunks) cudaFree(c.p); o->chunks.clear(); }
 extern "C" void cslam_optimizer_destroy(cslam_optimizer* o) {
     if (!o) return;
     cudaSetDevice(o->device);
     if (o->stream) cudaStreamSynchronize(o->stream);
-    free_pool(o);
+    release_pool(o);
     if (o->comm && nccl_api()) nccl_api()->CommDestroy(o->comm);
     if (o->stream) cudaStreamDestroy(o->stream);
     if (o->h_scal) cudaFreeHost(o->h_scal);
@@ -581,10 +584,16 @@ extern "C" int cslam_optimizer_init_nccl(cslam_optimizer* o, const uint8_t id128
 
 template <class T>
 static int dalloc(cslam_optimizer* o, T** p, size_t count, bool zero = false) {
-    void* q = nullptr;
-    CSLAM_CUDA(cudaMalloc(&q, std::max<size_t>(count, 1) * sizeof(T)));
-    if (zero) CSLAM_CUDA(cudaMemsetAsync(q, 0, std::max<size_t>(count, 1) * sizeof(T), o->stream));
-    o->pool.push_back(q); *p = (T*)q;
+    const size_t bytes = (std::max<size_t>(count, 1) * sizeof(T) + 255) & ~(size_t)255;
+    char* q = nullptr;
+    for (auto& c : o->chunks) if (c.size - c.used >= bytes) { q = c.p + c.used; c.used += bytes; break; }
+    if (!q) {
+        cslam_optimizer::Chunk c; c.size = std::max<size_t>(bytes, (size_t)64 << 20); c.used = bytes;
+        CSLAM_CUDA(cudaMalloc((void**)&c.p, c.size));
+        o->chunks.push_back(c); q = c.p;
+    }
+    if (zero) CSLAM_CUDA(cudaMemsetAsync(q, 0, bytes, o->stream));
+    *p = (T*)q;
     return 0;
 }
 template <class T>

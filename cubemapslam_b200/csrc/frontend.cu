@@ -12,7 +12,9 @@
 //   k_fast        per 30-px cell FAST-9/16 arc score, in-cell NMS, 20->7 threshold fallback, candidate append
 //   k_distribute  the reference's quadtree, restated as data-parallel rounds over nodes
 //   k_describe    IC angle + 7x7 Gaussian of the 43x43 neighbourhood + steered BRIEF, one warp per keypoint
+#include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 #include "common.cuh"
@@ -95,37 +97,56 @@ __global__ void __launch_bounds__(256) k_warp(const uint8_t* __restrict__ fishey
 }
 
 // ------------------------------------------------------------------------------------------------- k_pyramid
-// cv::resize(src,dst,sz,0,0,INTER_LINEAR) 8U model: 11-bit coefficients, horizontal int pass, vertical
-// (((b0*(r0>>4))>>16)+((b1*(r1>>4))>>16)+2)>>2.  One thread = 4 consecutive dst pixels (one u32 store).
-__global__ void __launch_bounds__(256) k_pyramid(const uint8_t* __restrict__ src, int sw, int sh, int spitch, uint8_t* __restrict__ dst, int dw, int dh,
+// cv::resize(src,dst,sz,0,0,INTER_LINEAR) 8U model: 11-bit coefficients, horizontal int pass H = S[s]*a0 + S[s+1]*a1,
+// vertical (((b0*(H0>>4))>>16)+((b1*(H1>>4))>>16)+2)>>2.  One thread = 4 consecutive dst pixels x PYR_RY dst rows:
+// the 8-byte source window of the 4 pixels is fetched with aligned 32-bit loads, the taps are gathered with PRMT and the
+// horizontal pass is two-tap IDP.2A (coefficient pair a0|a1<<16 straight from the table); a source row's H is reused by the
+// next dst row when it needs it again (1.2 source rows per dst row instead of 2).
+static const int PYR_RY = 8;
+__global__ void __launch_bounds__(128) k_pyramid(const uint8_t* __restrict__ src, int sw, int sh, int spitch, uint8_t* __restrict__ dst, int dw, int dh,
                                                  int dpitch, const uint16_t* __restrict__ xofs, const uint32_t* __restrict__ xab,
                                                  const uint16_t* __restrict__ yofs, const uint32_t* __restrict__ yab) {
     const int x4 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
-    const int y = blockIdx.y;
     if (x4 >= dw) return;
     const uint8_t* S = src + (size_t)blockIdx.z * spitch * sh;
     uint8_t* D = dst + (size_t)blockIdx.z * dpitch * dh;
-    const int sy0 = yofs[y], sy1 = min(sy0 + 1, sh - 1);
-    const uint32_t bb = yab[y];
-    const int b0 = (int)(bb & 0xffff), b1 = (int)(bb >> 16);
-    const uint8_t* R0 = S + (size_t)sy0 * spitch;
-    const uint8_t* R1 = S + (size_t)sy1 * spitch;
-    uint32_t out = 0;
+    int s0[4]; uint32_t ab[4];
+#pragma unroll
+    for (int k = 0; k < 4; k++) { const int x = min(x4 + k, dw - 1); s0[k] = xofs[x]; ab[k] = xab[x]; }
+    const int base = s0[0], al = base & ~3, sh8 = (base & 3) * 8;
+    // byte selectors into the 8-byte window starting at `base`: pair (left,right) per pixel; right = left when clamped at the last column
+    uint32_t sel01 = 0, sel23 = 0;
 #pragma unroll
     for (int k = 0; k < 4; k++) {
-        const int x = x4 + k;
-        if (x < dw) {
-            const int s0 = xofs[x], s1 = min(s0 + 1, sw - 1);
-            const uint32_t aa = xab[x];
-            const int a0 = (int)(aa & 0xffff), a1 = (int)(aa >> 16);
-            const int r0 = __ldg(R0 + s0) * a0 + __ldg(R0 + s1) * a1;
-            const int r1 = __ldg(R1 + s0) * a0 + __ldg(R1 + s1) * a1;
-            int v = (((b0 * (r0 >> 4)) >> 16) + ((b1 * (r1 >> 4)) >> 16) + 2) >> 2;
-            v = min(max(v, 0), 255);
-            out |= (uint32_t)v << (8 * k);
-        }
+        const uint32_t dl = (uint32_t)(s0[k] - base), dr = (s0[k] + 1 <= sw - 1) ? dl + 1 : dl;
+        const uint32_t pr = dl | (dr << 4);
+        if (k < 2) sel01 |= pr << (8 * k); else sel23 |= pr << (8 * (k - 2));
     }
-    *reinterpret_cast<uint32_t*>(D + (size_t)y * dpitch + x4) = out;   // pitch is a multiple of 128: padding absorbs the tail
+    const bool has1 = al + 4 < spitch, has2 = al + 8 < spitch;
+    auto hrow = [&](int sy, uint32_t (&H)[4]) {
+        const uint32_t* R = reinterpret_cast<const uint32_t*>(S + (size_t)sy * spitch + al);
+        const uint32_t w0 = __ldg(R), w1 = has1 ? __ldg(R + 1) : 0u, w2 = has2 ? __ldg(R + 2) : 0u;
+        const uint32_t lo = __funnelshift_r(w0, w1, sh8), hi = __funnelshift_r(w1, w2, sh8);
+        const uint32_t p01 = __byte_perm(lo, hi, sel01), p23 = __byte_perm(lo, hi, sel23);
+        H[0] = __dp2a_lo(ab[0], p01, 0u) >> 4; H[1] = __dp2a_hi(ab[1], p01, 0u) >> 4;
+        H[2] = __dp2a_lo(ab[2], p23, 0u) >> 4; H[3] = __dp2a_hi(ab[3], p23, 0u) >> 4;
+    };
+    const int y0 = blockIdx.y * PYR_RY, y1 = min(y0 + PYR_RY, dh);
+    int prevIdx = -1;
+    uint32_t prev[4] = {0, 0, 0, 0};
+    for (int y = y0; y < y1; y++) {
+        const int a = yofs[y], b = min(a + 1, sh - 1);
+        const uint32_t bb = yab[y];
+        const uint32_t b0 = bb & 0xffff, b1 = bb >> 16;
+        uint32_t r0[4], r1[4];
+        if (a == prevIdx) { r0[0] = prev[0]; r0[1] = prev[1]; r0[2] = prev[2]; r0[3] = prev[3]; } else hrow(a, r0);
+        if (b == a) { r1[0] = r0[0]; r1[1] = r0[1]; r1[2] = r0[2]; r1[3] = r0[3]; } else hrow(b, r1);
+        prevIdx = b; prev[0] = r1[0]; prev[1] = r1[1]; prev[2] = r1[2]; prev[3] = r1[3];
+        uint32_t out = 0;
+#pragma unroll
+        for (int k = 0; k < 4; k++) out |= ((((b0 * r0[k]) >> 16) + ((b1 * r1[k]) >> 16) + 2) >> 2) << (8 * k);   // <= 255, no clamp needed
+        *reinterpret_cast<uint32_t*>(D + (size_t)y * dpitch + x4) = out;   // pitch is a multiple of 128: padding absorbs the tail
+    }
 }
 
 // ------------------------------------------------------------------------------------------------- k_fast
@@ -170,14 +191,17 @@ __device__ __forceinline__ uint32_t fdiv_magic(int d) { return ((1u << 20) + d -
 //     (a suppressor needs s_n >= s), so the per-cell 20->7 fallback is a filter on that list
 //  C  compaction of the selected entries into the global candidate list (one global atomic per 256 entries)
 static const int FAST_KMAX = CG * (CELL_MAX / 2) * (CELL_MAX / 2);   // NMS survivors are pairwise non-adjacent
+static const int FAST_SW = FAST_TS / 2;                              // pair-words per score row
 
 __global__ void __launch_bounds__(256) k_fast(const uint8_t* __restrict__ img, LevelGeom g, int iniTh, int minTh, uint32_t* __restrict__ cand,
                                               uint32_t* __restrict__ candCount, int countStride, int* __restrict__ errFlag,
                                               const uint8_t* __restrict__ skip) {
     __shared__ __align__(16) uint8_t tile[FAST_TH * FAST_TS];
-    __shared__ __align__(16) uint8_t S[(CELL_MAX + 2) * FAST_TS];   // same column addressing as `tile`, row y+1
+    // score map, one u16 per pixel as u16x2 pair-words: word 2*wi (+1) of row y+1 holds tile columns 4*wi..4*wi+1 (+2..+3)
+    __shared__ __align__(16) uint32_t S2[(CELL_MAX + 2) * FAST_SW];
     __shared__ uint32_t klist[FAST_KMAX];                            // x | y<<8 | s<<16 | cell<<24
     __shared__ uint8_t cellInfo[FAST_TS];   // per detection column: cell index | 0x40 first column of its cell | 0x80 last
+    __shared__ uint32_t mskV[FAST_SW], mskL[FAST_SW], mskR[FAST_SW];  // per pair-word lane masks: valid column / has left / has right neighbour in its cell
     __shared__ int cnt20[CG];
     __shared__ int anyNonZero, nK, chunkBase;
     __shared__ int warpCnt[8];
@@ -207,11 +231,24 @@ __global__ void __launch_bounds__(256) k_fast(const uint8_t* __restrict__ img, L
     const int nx = tx1 - tx0 - 6, ny = nrows - 6;   // detection area
     const int xoff = tx0 - a0 + 3;                   // tile column of detection x = 0
     const int w0 = xoff >> 2, w1 = (xoff + nx + 3) >> 2, nw = w1 - w0;   // S/tile words covering the detection columns
-    // S must read 0 around the scored area: rows 0 and ny+1, and the words left/right of [w0,w1) in every row
-    for (int i = tid; i < 2 * (FAST_TS / 4); i += 256) reinterpret_cast<uint32_t*>(S + (i >= FAST_TS / 4 ? (ny + 1) * FAST_TS : 0))[i % (FAST_TS / 4)] = 0;
+    // S2 must read 0 around the scored area: rows 0 and ny+1, and the pair-words left/right of [2*w0, 2*w1) in every row
+    for (int i = tid; i < 2 * FAST_SW; i += 256) S2[(i >= FAST_SW ? (ny + 1) * FAST_SW : 0) + (i % FAST_SW)] = 0;
     for (int i = tid; i < 2 * ny; i += 256) {
-        const int r = (i >> 1) + 1, wsel = (i & 1) ? w1 : w0 - 1;
-        if (wsel >= 0 && wsel < FAST_TS / 4) reinterpret_cast<uint32_t*>(S + r * FAST_TS)[wsel] = 0;
+        const int r = (i >> 1) + 1, psel = (i & 1) ? 2 * w1 : 2 * w0 - 1;
+        if (psel >= 0 && psel < FAST_SW) S2[r * FAST_SW + psel] = 0;
+    }
+    for (int pw = tid; pw < FAST_SW; pw += 256) {
+        uint32_t v = 0, l = 0, r = 0;
+        for (int h = 0; h < 2; h++) {
+            const int x = 2 * pw + h - xoff;   // detection x of this lane
+            if (x >= 0 && x < nx) {
+                const int xl = x % g.wCell;
+                v |= 0xffffu << (16 * h);
+                if (xl != 0) l |= 0xffffu << (16 * h);
+                if (xl != g.wCell - 1 && x != nx - 1) r |= 0xffffu << (16 * h);
+            }
+        }
+        mskV[pw] = v; mskL[pw] = l; mskR[pw] = r;
     }
     for (int x = tid; x < nx; x += 256) {
         const int c = x / g.wCell, xl = x - c * g.wCell;
@@ -264,33 +301,38 @@ __global__ void __launch_bounds__(256) k_fast(const uint8_t* __restrict__ img, L
 #pragma unroll
             for (int k = 0; k < 16; k++) R[k] = __byte_perm(V[k], 0u, 0x4342);
             const uint32_t sB = arc_score_x2(R, __byte_perm(C, 0u, 0x4342));
-            const int c0 = wi * 4 - xoff;   // detection x of byte 0
-            uint32_t sc[4] = {sA & 0xffffu, sA >> 16, sB & 0xffffu, sB >> 16};
-            uint32_t outw = 0;
-#pragma unroll
-            for (int bq = 0; bq < 4; bq++)
-                if ((int)sc[bq] > minTh && (unsigned)(c0 + bq) < (unsigned)nx) outw |= sc[bq] << (8 * bq);
-            reinterpret_cast<uint32_t*>(S + (y + 1) * FAST_TS)[wi] = outw;
+            // scores <= minTh and columns outside the detection area read as 0
+            const uint32_t thr = (uint32_t)minTh;
+            uint32_t oA = ((sA & 0xffffu) > thr ? (sA & 0xffffu) : 0u) | ((sA >> 16) > thr ? (sA & 0xffff0000u) : 0u);
+            uint32_t oB = ((sB & 0xffffu) > thr ? (sB & 0xffffu) : 0u) | ((sB >> 16) > thr ? (sB & 0xffff0000u) : 0u);
+            uint32_t* Srow = S2 + (y + 1) * FAST_SW + 2 * wi;
+            Srow[0] = oA & mskV[2 * wi]; Srow[1] = oB & mskV[2 * wi + 1];
         }
     }
     __syncthreads();
-    // ---- B: NMS at minTh: keep s iff no same-cell neighbour n with s_n >= s (all stored scores are > minTh)
+    // ---- B: NMS at minTh in u16x2 lanes: keep s iff every same-cell neighbour is < s (all stored scores are > minTh)
     {
-        const int nitems = nw * ny;
+        const int np = 2 * nw, nitems = np * ny;
+        const uint32_t mgp = fdiv_magic(np);
         for (int it = tid; it < nitems; it += 256) {
-            const int y = fdiv_small(it, mgw), wi = w0 + (it - y * nw);
-            uint32_t wv = reinterpret_cast<const uint32_t*>(S + (y + 1) * FAST_TS)[wi];
-            while (wv) {
-                const int bq = (__ffs(wv) - 1) >> 3;
-                const int sv = (wv >> (8 * bq)) & 0xff, col = wi * 4 + bq, x = col - xoff;
-                wv &= ~(0xffu << (8 * bq));
-                const uint8_t* c = S + (y + 1) * FAST_TS + col;
-                const int info = cellInfo[x];
-                int m = max(c[-FAST_TS], c[FAST_TS]);
-                if (!(info & 0x40)) m = max(m, max(c[-1], max(c[-FAST_TS - 1], c[FAST_TS - 1])));
-                if (!(info & 0x80)) m = max(m, max(c[1], max(c[-FAST_TS + 1], c[FAST_TS + 1])));
-                if (m < sv) {
-                    const int cell = info & 0x3f;
+            const int y = fdiv_small(it, mgp), pw = 2 * w0 + (it - y * np);
+            const uint32_t* r1 = S2 + (y + 1) * FAST_SW + pw;
+            const uint32_t cur = r1[0];
+            if (cur == 0) continue;
+            const uint32_t* r0 = r1 - FAST_SW; const uint32_t* r2 = r1 + FAST_SW;
+            const uint32_t ml = mskL[pw], mr = mskR[pw];
+            const uint32_t a0 = pw > 0 ? r0[-1] : 0u, b0 = r0[0], c0 = r0[1];
+            const uint32_t a1 = pw > 0 ? r1[-1] : 0u, c1 = r1[1];
+            const uint32_t a2 = pw > 0 ? r2[-1] : 0u, b2 = r2[0], c2 = r2[1];
+            const uint32_t upL = __funnelshift_r(a0, b0, 16) & ml, upR = __funnelshift_r(b0, c0, 16) & mr;
+            const uint32_t cuL = __funnelshift_r(a1, cur, 16) & ml, cuR = __funnelshift_r(cur, c1, 16) & mr;
+            const uint32_t dnL = __funnelshift_r(a2, b2, 16) & ml, dnR = __funnelshift_r(b2, c2, 16) & mr;
+            const uint32_t M = __vimax3_u16x2(__vimax3_u16x2(upL, b0, upR), __vimax3_u16x2(cuL, cuR, b2), __vmaxu2(dnL, dnR));
+#pragma unroll
+            for (int h = 0; h < 2; h++) {
+                const int sv = (cur >> (16 * h)) & 0xffff, mv = (M >> (16 * h)) & 0xffff;
+                if (sv > mv) {
+                    const int x = 2 * pw + h - xoff, cell = cellInfo[x] & 0x3f;
                     const int pos = atomicAdd(&nK, 1);
                     if (pos >= FAST_KMAX) *errFlag = CSLAM_E_CAPACITY;
                     else klist[pos] = (uint32_t)x | ((uint32_t)y << 8) | ((uint32_t)sv << 16) | ((uint32_t)cell << 24);
@@ -611,10 +653,12 @@ struct DescribeArgs {
     int* errFlag;
 };
 
+static const int DP_STRIDE = 48;                 // patch row stride (bytes): 43 px + up to 3 bytes of word misalignment
+static const int DH_STRIDE = 44;                 // transposed H: u16 per row index, per column
 __global__ void __launch_bounds__(DESC_WARPS * 32) k_describe(DescribeArgs A) {
-    __shared__ uint8_t s_patch[DESC_WARPS][43 * 44];
-    __shared__ uint16_t s_h[DESC_WARPS][43 * 38];
-    __shared__ uint8_t s_blur[DESC_WARPS][37 * 40];
+    __shared__ __align__(16) uint8_t s_patch[DESC_WARPS][43 * DP_STRIDE + 16];
+    __shared__ __align__(16) uint16_t s_ht[DESC_WARPS][37 * DH_STRIDE + 8];
+    __shared__ __align__(16) uint8_t s_blur[DESC_WARPS][37 * 40];
     __shared__ signed char s_pat[1024];
     const int level = blockIdx.y, frame = blockIdx.z;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -633,12 +677,23 @@ __global__ void __launch_bounds__(DESC_WARPS * 32) k_describe(DescribeArgs A) {
     const uint32_t v = A.kept[((size_t)frame * A.L.nlevels + level) * A.keptCap + slot];
     const int kx = v & 0xfff, ky = (v >> 12) & 0xfff, resp = v >> 24;
 
-    // ---- 43x43 neighbourhood (REFLECT_101 at the level edges, like the blur of the apron-less clone)
+    // ---- 43x43 neighbourhood -> P[r][po + c] (REFLECT_101 at the level edges, like the blur of the apron-less clone)
     uint8_t* P = s_patch[warp];
-    for (int i = lane; i < 43 * 43; i += 32) {
-        const int r = i / 43, c = i - r * 43;
-        const int yy = reflect101(ky - 21 + r, g.h), xx = reflect101(kx - 21 + c, g.w);
-        P[r * 44 + c] = __ldg(I + (size_t)yy * g.pitch + xx);
+    int po;
+    if (kx >= 21 && ky >= 21 && kx + 21 < g.w && ky + 21 < g.h) {
+        // interior: aligned 32-bit loads, two rows (16 lanes each, 12 words used) per step
+        const int x0 = kx - 21; po = x0 & 3;
+        const int wd = lane & 15, rs = lane >> 4;
+        const uint8_t* base = I + (size_t)(ky - 21) * g.pitch + (x0 & ~3);
+        for (int r = rs; r < 43; r += 2)
+            if (wd < 12) reinterpret_cast<uint32_t*>(P + r * DP_STRIDE)[wd] = __ldg(reinterpret_cast<const uint32_t*>(base + (size_t)r * g.pitch) + wd);
+    } else {
+        po = 0;
+        for (int i = lane; i < 43 * 43; i += 32) {
+            const int r = i / 43, c = i - r * 43;
+            const int yy = reflect101(ky - 21 + r, g.h), xx = reflect101(kx - 21 + c, g.w);
+            P[r * DP_STRIDE + c] = __ldg(I + (size_t)yy * g.pitch + xx);
+        }
     }
     __syncwarp();
     // ---- IC_Angle on the unblurred patch: lane = column u in [-15,15]
@@ -649,7 +704,7 @@ __global__ void __launch_bounds__(DESC_WARPS * 32) k_describe(DescribeArgs A) {
         for (int vv = -HALF_PATCH; vv <= HALF_PATCH; vv++) {
             const int av = vv < 0 ? -vv : vv;
             if ((u < 0 ? -u : u) <= c_umax[av]) {
-                const int val = P[(21 + vv) * 44 + 21 + u];
+                const int val = P[(21 + vv) * DP_STRIDE + po + 21 + u];
                 colsum += val; m01 += vv * val;
             }
         }
@@ -658,20 +713,45 @@ __global__ void __launch_bounds__(DESC_WARPS * 32) k_describe(DescribeArgs A) {
 #pragma unroll
     for (int o = 16; o; o >>= 1) { m10 += __shfl_xor_sync(0xffffffffu, m10, o); m01 += __shfl_xor_sync(0xffffffffu, m01, o); }
     const float angle = fast_atan2_deg((float)m01, (float)m10);
-    // ---- 7x7 sigma-2 Gaussian, OpenCV 8.8 fixed point [18,34,48,56,48,34,18], only where BRIEF can sample (+-18)
-    uint16_t* Hh = s_h[warp];
-    for (int i = lane; i < 43 * 37; i += 32) {
-        const int r = i / 37, c = i - r * 37;
-        const uint8_t* q = P + r * 44 + c;
-        Hh[r * 38 + c] = (uint16_t)(18 * (q[0] + q[6]) + 34 * (q[1] + q[5]) + 48 * (q[2] + q[4]) + 56 * q[3]);
+    // ---- 7x7 sigma-2 Gaussian, OpenCV 8.8 fixed point [18,34,48,56,48,34,18], only where BRIEF can sample (+-18).
+    // Horizontal: 4 outputs per item from one 12-byte window with IDP.4A; stored transposed (Ht[c][r], u16, exact: <= 65280).
+    uint16_t* Ht = s_ht[warp];
+    {
+        const uint32_t K0123 = 18u | (34u << 8) | (48u << 16) | (56u << 24), K456 = 48u | (34u << 8) | (18u << 16);
+        for (int it = lane; it < 43 * 10; it += 32) {
+            const int r = it / 10, cg = it - r * 10;
+            const int bidx = po + 4 * cg;
+            const uint32_t* W = reinterpret_cast<const uint32_t*>(P + r * DP_STRIDE) + (bidx >> 2);
+            const int sh = (bidx & 3) * 8;
+            const uint32_t w0 = W[0], w1 = W[1], w2 = W[2], w3 = W[3];
+            const uint32_t x0 = __funnelshift_r(w0, w1, sh), x1 = __funnelshift_r(w1, w2, sh), x2 = __funnelshift_r(w2, w3, sh);
+            uint32_t h[4];
+            h[0] = __dp4a(x0, K0123, __dp4a(x1, K456, 0u));
+            h[1] = __dp4a(__funnelshift_r(x0, x1, 8), K0123, __dp4a(__funnelshift_r(x1, x2, 8), K456, 0u));
+            h[2] = __dp4a(__funnelshift_r(x0, x1, 16), K0123, __dp4a(__funnelshift_r(x1, x2, 16), K456, 0u));
+            h[3] = __dp4a(__funnelshift_r(x0, x1, 24), K0123, __dp4a(__funnelshift_r(x1, x2, 24), K456, 0u));
+#pragma unroll
+            for (int j = 0; j < 4; j++) if (4 * cg + j < 37) Ht[(4 * cg + j) * DH_STRIDE + r] = (uint16_t)h[j];
+        }
     }
     __syncwarp();
+    // Vertical: 4 output rows of one column per item from five u16x2 words with IDP.2A; dst = (V + 32768) >> 16
     uint8_t* Bl = s_blur[warp];
-    for (int i = lane; i < 37 * 37; i += 32) {
-        const int r = i / 37, c = i - r * 37;
-        const uint16_t* q = Hh + r * 38 + c;
-        const uint32_t s = 18u * (q[0] + q[6 * 38]) + 34u * (q[38] + q[5 * 38]) + 48u * (q[2 * 38] + q[4 * 38]) + 56u * q[3 * 38];
-        Bl[r * 40 + c] = (uint8_t)((s + 32768u) >> 16);
+    {
+        const uint32_t K01 = 18u | (34u << 8), K23 = 48u | (56u << 8), K45 = 48u | (34u << 8);
+        for (int it = lane; it < 37 * 10; it += 32) {
+            const int c = it / 10, rg = it - c * 10;
+            const uint32_t* Hw = reinterpret_cast<const uint32_t*>(Ht + c * DH_STRIDE) + 2 * rg;
+            const uint32_t q0 = Hw[0], q1 = Hw[1], q2 = Hw[2], q3 = Hw[3], q4 = Hw[4];
+            const uint32_t s01 = __funnelshift_r(q0, q1, 16), s12 = __funnelshift_r(q1, q2, 16), s23 = __funnelshift_r(q2, q3, 16), s34 = __funnelshift_r(q3, q4, 16);
+            uint32_t o[4];
+            o[0] = __dp2a_lo(q0, K01, __dp2a_lo(q1, K23, __dp2a_lo(q2, K45, 18u * (q3 & 0xffffu))));
+            o[1] = __dp2a_lo(s01, K01, __dp2a_lo(s12, K23, __dp2a_lo(s23, K45, 18u * (q3 >> 16))));
+            o[2] = __dp2a_lo(q1, K01, __dp2a_lo(q2, K23, __dp2a_lo(q3, K45, 18u * (q4 & 0xffffu))));
+            o[3] = __dp2a_lo(s12, K01, __dp2a_lo(s23, K23, __dp2a_lo(s34, K45, 18u * (q4 >> 16))));
+#pragma unroll
+            for (int j = 0; j < 4; j++) if (4 * rg + j < 37) Bl[(4 * rg + j) * 40 + c] = (uint8_t)((o[j] + 32768u) >> 16);
+        }
     }
     __syncwarp();
     // ---- steered BRIEF: lane = output byte
@@ -720,6 +800,9 @@ struct cslam_frontend {
     int* d_err = nullptr;
     uint8_t* h_pin_in = nullptr; cslam_keypoint* h_pin_kps = nullptr; uint8_t* h_pin_desc = nullptr; int32_t* h_pin_n = nullptr; int* h_pin_err = nullptr;
     std::vector<void*> owned;
+    static const int MAX_LANES = 4;
+    cudaStream_t lane[MAX_LANES] = {nullptr, nullptr, nullptr, nullptr}; cudaEvent_t evLane[MAX_LANES] = {nullptr, nullptr, nullptr, nullptr}; cudaEvent_t evFork = nullptr;
+    int devLanes = 2;                // lanes used by cslam_frontend_run_dev (env CSLAM_DEV_LANES)
     int64_t launches = 0;
     int lastBatch = 0;
     // optional per-kernel timing (cslam_frontend_set_timing): events between launches, accumulated per kernel kind
@@ -731,10 +814,10 @@ struct cslam_frontend {
 
 enum { KIND_WARP = 0, KIND_PYRAMID, KIND_FAST, KIND_DISTRIBUTE, KIND_DESCRIBE, KIND_END, KIND_COUNT };
 static const char* kKindNames[KIND_COUNT] = {"k_warp", "k_pyramid", "k_fast", "k_distribute", "k_describe", "end"};
-static inline void mark(cslam_frontend* fe, int kind) {
+static inline void mark(cslam_frontend* fe, cudaStream_t st, int kind) {
     if (kind != KIND_END) fe->launches++;
     if (!fe->timing || fe->evUsed >= (int)fe->ev.size()) return;
-    cudaEventRecord(fe->ev[fe->evUsed], fe->stream);
+    cudaEventRecord(fe->ev[fe->evUsed], st);
     fe->evKind[fe->evUsed++] = kind;
 }
 static void collect_timing(cslam_frontend* fe) {
@@ -826,7 +909,7 @@ extern "C" int cslam_frontend_create(cslam_frontend** out, int device, const csl
     if (device < 0 || device >= ndev) { set_error("device %d out of range (%d devices)", device, ndev); return CSLAM_E_BADARG; }
     if (cam->face_w != cam->face_h || cam->face_w <= 0) { set_error("cube faces must be square (got %dx%d)", cam->face_w, cam->face_h); return CSLAM_E_BADARG; }
     if (3 * cam->face_w > 4095 || cam->Iw * 32 > 65535 || cam->Ih * 32 > 65535) { set_error("image too large for the packed coordinate formats"); return CSLAM_E_BADARG; }
-    if (orb->nlevels < 1 || orb->nlevels > MAX_LEVELS || orb->nfeatures < 1 || orb->scale_factor <= 1.f) { set_error("bad ORB parameters"); return CSLAM_E_BADARG; }
+    if (orb->nlevels < 1 || orb->nlevels > MAX_LEVELS || orb->nfeatures < 1 || orb->scale_factor <= 1.f || orb->scale_factor > 2.f) { set_error("bad ORB parameters (need 1 < scaleFactor <= 2)"); return CSLAM_E_BADARG; }
     CSLAM_CUDA(cudaSetDevice(device));
     cslam_frontend* fe = new cslam_frontend;
     fe->device = device; fe->cam = *cam; fe->orb = *orb; fe->maxBatch = max_batch;
@@ -851,6 +934,10 @@ extern "C" int cslam_frontend_create(cslam_frontend** out, int device, const csl
     int rc = 0;
     auto fail = [&](int code) { cslam_frontend_destroy(fe); return code; };
     if (cudaStreamCreateWithFlags(&fe->stream, cudaStreamNonBlocking) != cudaSuccess) { set_error("cudaStreamCreate failed"); return fail(CSLAM_E_CUDA); }
+    for (int i = 0; i < cslam_frontend::MAX_LANES; i++)
+        if (cudaStreamCreateWithFlags(&fe->lane[i], cudaStreamNonBlocking) != cudaSuccess || cudaEventCreateWithFlags(&fe->evLane[i], cudaEventDisableTiming) != cudaSuccess) { set_error("lane stream creation failed"); return fail(CSLAM_E_CUDA); }
+    if (cudaEventCreateWithFlags(&fe->evFork, cudaEventDisableTiming) != cudaSuccess) { set_error("event creation failed"); return fail(CSLAM_E_CUDA); }
+    if (const char* e = getenv("CSLAM_DEV_LANES")) fe->devLanes = std::max(1, std::min(atoi(e), (int)cslam_frontend::MAX_LANES));
     if (cudaMemcpyToSymbol(c_umax, fe->umax, sizeof(fe->umax)) != cudaSuccess) { set_error("cudaMemcpyToSymbol failed"); return fail(CSLAM_E_CUDA); }
     // ---- level geometry (ComputePyramid :930-936, ComputeKeyPointsOctTree :747-761)
     std::memset(&fe->L, 0, sizeof(fe->L));
@@ -872,7 +959,7 @@ extern "C" int cslam_frontend_create(cslam_frontend** out, int device, const csl
         g.quota = fe->perLevel[l]; maxQuota = std::max(maxQuota, g.quota);
         g.candCap = std::max(4096, g.nColsEff * g.nRowsEff * 32);
         g.scale = fe->scale[l]; g.sizeF = (float)(int)(PATCH_SIZE * fe->scale[l]);
-        if ((rc = dev_alloc(fe, &fe->L.img[l], (size_t)max_batch * g.pitch * g.h))) return fail(rc);
+        if ((rc = dev_alloc(fe, &fe->L.img[l], (size_t)max_batch * g.pitch * g.h + 256))) return fail(rc);   // slack: word loads may run a few bytes past the last row
         if ((rc = dev_alloc(fe, &fe->L.cand[l], (size_t)max_batch * g.candCap, false))) return fail(rc);
         if ((rc = dev_alloc(fe, &fe->L.pnode[l], (size_t)max_batch * g.candCap, false))) return fail(rc);
         if (l > 0) {
@@ -975,7 +1062,10 @@ extern "C" int cslam_frontend_create(cslam_frontend** out, int device, const csl
 extern "C" void cslam_frontend_destroy(cslam_frontend* fe) {
     if (!fe) return;
     cudaSetDevice(fe->device);
-    if (fe->stream) { cudaStreamSynchronize(fe->stream); cudaStreamDestroy(fe->stream); }
+    cudaDeviceSynchronize();
+    for (int i = 0; i < cslam_frontend::MAX_LANES; i++) { if (fe->lane[i]) cudaStreamDestroy(fe->lane[i]); if (fe->evLane[i]) cudaEventDestroy(fe->evLane[i]); }
+    if (fe->evFork) cudaEventDestroy(fe->evFork);
+    if (fe->stream) cudaStreamDestroy(fe->stream);
     for (void* p : fe->owned) cudaFree(p);
     for (auto& e : fe->ev) cudaEventDestroy(e);
     if (fe->h_pin_in) cudaFreeHost(fe->h_pin_in);
@@ -1020,49 +1110,57 @@ extern "C" int cslam_frontend_sync(cslam_frontend* fe) {
     return CSLAM_OK;
 }
 
-static int launch_warp(cslam_frontend* fe, const uint8_t* d_fisheye, int batch) {
+// Frame range [f0, f0+cnt) of the per-batch buffers, for one lane
+static DevLevels shifted(const cslam_frontend* fe, int f0) {
+    DevLevels L = fe->L;
+    for (int l = 0; l < L.nlevels; l++) {
+        const LevelGeom& g = L.g[l];
+        L.img[l] += (size_t)f0 * g.pitch * g.h; L.cand[l] += (size_t)f0 * g.candCap; L.pnode[l] += (size_t)f0 * g.candCap;
+    }
+    return L;
+}
+
+static int launch_warp(cslam_frontend* fe, cudaStream_t st, const uint8_t* d_fisheye, int f0, int cnt) {
     const int FPT = 4;
     if (!fe->d_map) { set_error("this front end was created without fisheye geometry (Iw/Ih = 0): no warp"); return CSLAM_E_BADARG; }
-    if (fe->cornersDirty) {   // the warp never writes the 4 corner tiles; they must read as the reference's zeroed canvas
-        CSLAM_CUDA(cudaMemsetAsync(fe->L.img[0], 0, (size_t)fe->maxBatch * fe->L.g[0].pitch * fe->CH, fe->stream));
-        fe->cornersDirty = false;
-    }
-    dim3 grid(cdiv(fe->W, 256), fe->H, 5 * cdiv(batch, FPT));
-    mark(fe, KIND_WARP);
-    k_warp<FPT><<<grid, 256, 0, fe->stream>>>(d_fisheye, fe->cam.Iw, fe->cam.Ih, fe->d_map, fe->W, fe->L.img[0], fe->L.g[0].pitch,
-                                               (size_t)fe->L.g[0].pitch * fe->CH, batch);
+    const size_t cframe = (size_t)fe->L.g[0].pitch * fe->CH;
+    dim3 grid(cdiv(fe->W, 256), fe->H, 5 * cdiv(cnt, FPT));
+    mark(fe, st, KIND_WARP);
+    k_warp<FPT><<<grid, 256, 0, st>>>(d_fisheye, fe->cam.Iw, fe->cam.Ih, fe->d_map, fe->W, fe->L.img[0] + (size_t)f0 * cframe, fe->L.g[0].pitch, cframe, cnt);
     CSLAM_CUDA(cudaGetLastError());
     return 0;
 }
 
-static int launch_extract(cslam_frontend* fe, int batch, cslam_keypoint* d_kps, uint8_t* d_desc, int32_t* d_nout) {
+static int launch_extract(cslam_frontend* fe, cudaStream_t st, int f0, int cnt, cslam_keypoint* d_kps, uint8_t* d_desc, int32_t* d_nout, bool useSkip) {
     const int nl = fe->L.nlevels;
-    fe->lastBatch = batch;
-    CSLAM_CUDA(cudaMemsetAsync(fe->d_candCount, 0, (size_t)batch * nl * sizeof(uint32_t), fe->stream));
+    const DevLevels L = shifted(fe, f0);
+    uint32_t* candCount = fe->d_candCount + (size_t)f0 * nl;
+    CSLAM_CUDA(cudaMemsetAsync(candCount, 0, (size_t)cnt * nl * sizeof(uint32_t), st));
     for (int l = 1; l < nl; l++) {
-        const LevelGeom& s = fe->L.g[l - 1]; const LevelGeom& d = fe->L.g[l];
-        dim3 grid(cdiv(cdiv(d.w, 4), 256), d.h, batch);
-        mark(fe, KIND_PYRAMID);
-        k_pyramid<<<grid, 256, 0, fe->stream>>>(fe->L.img[l - 1], s.w, s.h, s.pitch, fe->L.img[l], d.w, d.h, d.pitch, fe->L.xofs[l], fe->L.xab[l], fe->L.yofs[l], fe->L.yab[l]);
+        const LevelGeom& s = L.g[l - 1]; const LevelGeom& d = L.g[l];
+        dim3 grid(cdiv(cdiv(d.w, 4), 128), cdiv(d.h, PYR_RY), cnt);
+        mark(fe, st, KIND_PYRAMID);
+        k_pyramid<<<grid, 128, 0, st>>>(L.img[l - 1], s.w, s.h, s.pitch, L.img[l], d.w, d.h, d.pitch, L.xofs[l], L.xab[l], L.yofs[l], L.yab[l]);
     }
     for (int l = 0; l < nl; l++) {
-        const LevelGeom& g = fe->L.g[l];
-        dim3 grid(cdiv(g.nColsEff, CG), g.nRowsEff, batch);
-        mark(fe, KIND_FAST);
-        k_fast<<<grid, 256, 0, fe->stream>>>(fe->L.img[l], g, fe->orb.ini_th_fast, fe->orb.min_th_fast, fe->L.cand[l], fe->d_candCount + l, nl, fe->d_err, fe->cornersDirty ? nullptr : fe->L.skip[l]);
+        const LevelGeom& g = L.g[l];
+        dim3 grid(cdiv(g.nColsEff, CG), g.nRowsEff, cnt);
+        mark(fe, st, KIND_FAST);
+        k_fast<<<grid, 256, 0, st>>>(L.img[l], g, fe->orb.ini_th_fast, fe->orb.min_th_fast, L.cand[l], candCount + l, nl, fe->d_err, useSkip ? L.skip[l] : nullptr);
     }
     CSLAM_CUDA(cudaGetLastError());
     DistributeArgs da;
-    da.L = fe->L; da.candCount = fe->d_candCount; da.kept = fe->d_kept; da.keptCount = fe->d_keptCount; da.mask = fe->d_mask; da.maskPitch = fe->maskPitch;
+    da.L = L; da.candCount = candCount; da.kept = fe->d_kept + (size_t)f0 * nl * fe->keptCap; da.keptCount = fe->d_keptCount + (size_t)f0 * nl;
+    da.mask = fe->d_mask; da.maskPitch = fe->maskPitch;
     da.imgW = fe->CW; da.imgH = fe->CH; da.faceW = fe->W; da.faceH = fe->H; da.keptCap = fe->keptCap; da.M = fe->M; da.errFlag = fe->d_err;
-    mark(fe, KIND_DISTRIBUTE);
-    k_distribute<<<dim3(nl, batch), 256, fe->distributeSmem, fe->stream>>>(da);
+    mark(fe, st, KIND_DISTRIBUTE);
+    k_distribute<<<dim3(nl, cnt), 256, fe->distributeSmem, st>>>(da);
     DescribeArgs ds;
-    ds.L = fe->L; ds.kept = fe->d_kept; ds.keptCount = fe->d_keptCount; ds.keptCap = fe->keptCap; ds.kps = d_kps; ds.desc = d_desc; ds.nOut = d_nout; ds.kpCap = fe->kpCap;
+    ds.L = L; ds.kept = da.kept; ds.keptCount = da.keptCount; ds.keptCap = fe->keptCap; ds.kps = d_kps; ds.desc = d_desc; ds.nOut = d_nout; ds.kpCap = fe->kpCap;
     ds.errFlag = fe->d_err;
-    mark(fe, KIND_DESCRIBE);
-    k_describe<<<dim3(cdiv(fe->keptCap, DESC_WARPS), nl, batch), DESC_WARPS * 32, 0, fe->stream>>>(ds);
-    mark(fe, KIND_END);
+    mark(fe, st, KIND_DESCRIBE);
+    k_describe<<<dim3(cdiv(fe->keptCap, DESC_WARPS), nl, cnt), DESC_WARPS * 32, 0, st>>>(ds);
+    mark(fe, st, KIND_END);
     CSLAM_CUDA(cudaGetLastError());
     return 0;
 }
@@ -1073,13 +1171,46 @@ static int check_batch(cslam_frontend* fe, int batch, const void* a, const void*
     return 0;
 }
 
+static bool is_pinned(const void* p) {
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return at.type == cudaMemoryTypeHost;
+}
+
+// Lanes: the batch is cut into contiguous frame ranges, each enqueued on its own stream (forked from / joined into the
+// front end's main stream). Different lanes touch disjoint slices of every buffer, so the copy engines and the
+// latency-bound k_distribute of one lane overlap with the ALU-bound kernels of the others.
+static int fork_lanes(cslam_frontend* fe, int nl) {
+    CSLAM_CUDA(cudaEventRecord(fe->evFork, fe->stream));
+    for (int i = 0; i < nl; i++) CSLAM_CUDA(cudaStreamWaitEvent(fe->lane[i], fe->evFork, 0));
+    return 0;
+}
+static int join_lanes(cslam_frontend* fe, int nl) {
+    for (int i = 0; i < nl; i++) { CSLAM_CUDA(cudaEventRecord(fe->evLane[i], fe->lane[i])); CSLAM_CUDA(cudaStreamWaitEvent(fe->stream, fe->evLane[i], 0)); }
+    return 0;
+}
+static int prepare_level0(cslam_frontend* fe, bool fromWarp) {
+    if (fromWarp && fe->cornersDirty) {   // the warp never writes the 4 corner tiles; they must read as the reference's zeroed canvas
+        CSLAM_CUDA(cudaMemsetAsync(fe->L.img[0], 0, (size_t)fe->maxBatch * fe->L.g[0].pitch * fe->CH, fe->stream));
+        fe->cornersDirty = false;
+    }
+    if (!fromWarp) fe->cornersDirty = true;
+    return 0;
+}
+static int lanes_for(const cslam_frontend* fe, int batch, int want) {
+    if (fe->timing) return 1;
+    return std::max(1, std::min(std::min(want, cslam_frontend::MAX_LANES), batch));
+}
+
 extern "C" int cslam_warp(cslam_frontend* fe, const uint8_t* fisheye, int batch, uint8_t* canvas, int canvas_pitch) {
     int rc = check_batch(fe, batch, fisheye, canvas);
     if (rc) return rc;
+    if ((rc = prepare_level0(fe, true))) return rc;
     const size_t fb = (size_t)fe->cam.Iw * fe->cam.Ih * batch;
-    std::memcpy(fe->h_pin_in, fisheye, fb);
-    CSLAM_CUDA(cudaMemcpyAsync(fe->d_fisheye, fe->h_pin_in, fb, cudaMemcpyHostToDevice, fe->stream));
-    if ((rc = launch_warp(fe, fe->d_fisheye, batch))) return rc;
+    const uint8_t* src = fisheye;
+    if (!is_pinned(fisheye)) { std::memcpy(fe->h_pin_in, fisheye, fb); src = fe->h_pin_in; }
+    CSLAM_CUDA(cudaMemcpyAsync(fe->d_fisheye, src, fb, cudaMemcpyHostToDevice, fe->stream));
+    if ((rc = launch_warp(fe, fe->stream, fe->d_fisheye, 0, batch))) return rc;
     // the reference writes only the five face ROIs; corner tiles of the caller's canvas are left untouched
     const int W = fe->W, pitch = fe->L.g[0].pitch;
     const int tc[5] = {1, 0, 2, 1, 1}, tr[5] = {1, 1, 1, 0, 2};
@@ -1090,16 +1221,41 @@ extern "C" int cslam_warp(cslam_frontend* fe, const uint8_t* fisheye, int batch,
     return cslam_frontend_sync(fe);
 }
 
-static int download_results(cslam_frontend* fe, int batch, cslam_keypoint* kps, uint8_t* desc, int32_t* n_out) {
-    const size_t nk = (size_t)batch * fe->kpCap;
-    CSLAM_CUDA(cudaMemcpyAsync(fe->h_pin_kps, fe->d_kps, nk * sizeof(cslam_keypoint), cudaMemcpyDeviceToHost, fe->stream));
-    CSLAM_CUDA(cudaMemcpyAsync(fe->h_pin_desc, fe->d_desc, nk * 32, cudaMemcpyDeviceToHost, fe->stream));
-    CSLAM_CUDA(cudaMemcpyAsync(fe->h_pin_n, fe->d_nout, batch * sizeof(int32_t), cudaMemcpyDeviceToHost, fe->stream));
-    int rc = cslam_frontend_sync(fe);
-    if (rc) return rc;
-    std::memcpy(kps, fe->h_pin_kps, nk * sizeof(cslam_keypoint));
-    std::memcpy(desc, fe->h_pin_desc, nk * 32);
-    std::memcpy(n_out, fe->h_pin_n, batch * sizeof(int32_t));
+// host entry points: H2D -> kernels -> D2H per lane; caller buffers are used directly when they are page-locked
+static int run_host(cslam_frontend* fe, const uint8_t* in, size_t inFrameBytes, int inPitch, bool fromWarp, int batch, cslam_keypoint* kps, uint8_t* desc, int32_t* n_out) {
+    int rc;
+    if ((rc = prepare_level0(fe, fromWarp))) return rc;
+    const int nlanes = lanes_for(fe, batch, 4);
+    const bool pinIn = is_pinned(in), pinK = is_pinned(kps), pinD = is_pinned(desc), pinN = is_pinned(n_out);
+    const size_t nk = (size_t)fe->kpCap;
+    if ((rc = fork_lanes(fe, nlanes))) return rc;
+    for (int ln = 0; ln < nlanes; ln++) {
+        const int f0 = (int)((long long)batch * ln / nlanes), f1 = (int)((long long)batch * (ln + 1) / nlanes), cnt = f1 - f0;
+        if (cnt <= 0) continue;
+        cudaStream_t st = fe->lane[ln];
+        if (fromWarp) {
+            const uint8_t* src = in + (size_t)f0 * inFrameBytes;
+            if (!pinIn) { std::memcpy(fe->h_pin_in + (size_t)f0 * inFrameBytes, src, (size_t)cnt * inFrameBytes); src = fe->h_pin_in + (size_t)f0 * inFrameBytes; }
+            uint8_t* dfe = fe->d_fisheye + (size_t)f0 * inFrameBytes;
+            CSLAM_CUDA(cudaMemcpyAsync(dfe, src, (size_t)cnt * inFrameBytes, cudaMemcpyHostToDevice, st));
+            if ((rc = launch_warp(fe, st, dfe, f0, cnt))) return rc;
+        } else {
+            const int pitch = fe->L.g[0].pitch;
+            CSLAM_CUDA(cudaMemcpy2DAsync(fe->L.img[0] + (size_t)f0 * pitch * fe->CH, pitch, in + (size_t)f0 * inPitch * fe->CH, inPitch, fe->CW, (size_t)fe->CH * cnt,
+                                         cudaMemcpyHostToDevice, st));
+        }
+        if ((rc = launch_extract(fe, st, f0, cnt, fe->d_kps + (size_t)f0 * nk, fe->d_desc + (size_t)f0 * nk * 32, fe->d_nout + f0, fromWarp))) return rc;
+        CSLAM_CUDA(cudaMemcpyAsync((pinK ? kps : fe->h_pin_kps) + (size_t)f0 * nk, fe->d_kps + (size_t)f0 * nk, (size_t)cnt * nk * sizeof(cslam_keypoint), cudaMemcpyDeviceToHost, st));
+        CSLAM_CUDA(cudaMemcpyAsync((pinD ? desc : fe->h_pin_desc) + (size_t)f0 * nk * 32, fe->d_desc + (size_t)f0 * nk * 32, (size_t)cnt * nk * 32, cudaMemcpyDeviceToHost, st));
+        CSLAM_CUDA(cudaMemcpyAsync((pinN ? n_out : fe->h_pin_n) + f0, fe->d_nout + f0, (size_t)cnt * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    }
+    if ((rc = join_lanes(fe, nlanes))) return rc;
+    fe->lastBatch = batch;
+    if ((rc = cslam_frontend_sync(fe))) return rc;
+    const size_t tot = (size_t)batch * nk;
+    if (!pinK) std::memcpy(kps, fe->h_pin_kps, tot * sizeof(cslam_keypoint));
+    if (!pinD) std::memcpy(desc, fe->h_pin_desc, tot * 32);
+    if (!pinN) std::memcpy(n_out, fe->h_pin_n, batch * sizeof(int32_t));
     return CSLAM_OK;
 }
 
@@ -1107,31 +1263,32 @@ extern "C" int cslam_orb_extract(cslam_frontend* fe, const uint8_t* canvas, int 
     int rc = check_batch(fe, batch, canvas, kps);
     if (rc) return rc;
     if (!desc || !n_out || canvas_pitch < fe->CW) { set_error("cslam_orb_extract: bad argument"); return CSLAM_E_BADARG; }
-    const int pitch = fe->L.g[0].pitch;
-    CSLAM_CUDA(cudaMemcpy2DAsync(fe->L.img[0], pitch, canvas, canvas_pitch, fe->CW, (size_t)fe->CH * batch, cudaMemcpyHostToDevice, fe->stream));
-    fe->cornersDirty = true;
-    if ((rc = launch_extract(fe, batch, fe->d_kps, fe->d_desc, fe->d_nout))) return rc;
-    return download_results(fe, batch, kps, desc, n_out);
+    return run_host(fe, canvas, 0, canvas_pitch, false, batch, kps, desc, n_out);
 }
 
 extern "C" int cslam_frontend_run(cslam_frontend* fe, const uint8_t* fisheye, int batch, cslam_keypoint* kps, uint8_t* desc, int32_t* n_out) {
     int rc = check_batch(fe, batch, fisheye, kps);
     if (rc) return rc;
     if (!desc || !n_out) { set_error("cslam_frontend_run: null output"); return CSLAM_E_BADARG; }
-    const size_t fb = (size_t)fe->cam.Iw * fe->cam.Ih * batch;
-    std::memcpy(fe->h_pin_in, fisheye, fb);
-    CSLAM_CUDA(cudaMemcpyAsync(fe->d_fisheye, fe->h_pin_in, fb, cudaMemcpyHostToDevice, fe->stream));
-    if ((rc = launch_warp(fe, fe->d_fisheye, batch))) return rc;
-    if ((rc = launch_extract(fe, batch, fe->d_kps, fe->d_desc, fe->d_nout))) return rc;
-    return download_results(fe, batch, kps, desc, n_out);
+    return run_host(fe, fisheye, (size_t)fe->cam.Iw * fe->cam.Ih, 0, true, batch, kps, desc, n_out);
 }
 
 extern "C" int cslam_frontend_run_dev(cslam_frontend* fe, const uint8_t* fisheye_dev, int batch, cslam_keypoint* kps_dev, uint8_t* desc_dev, int32_t* n_out_dev) {
     int rc = check_batch(fe, batch, fisheye_dev, kps_dev);
     if (rc) return rc;
     if (!desc_dev || !n_out_dev) { set_error("cslam_frontend_run_dev: null output"); return CSLAM_E_BADARG; }
-    if ((rc = launch_warp(fe, fisheye_dev, batch))) return rc;
-    return launch_extract(fe, batch, kps_dev, desc_dev, n_out_dev);
+    if ((rc = prepare_level0(fe, true))) return rc;
+    const int nlanes = lanes_for(fe, batch, fe->devLanes);
+    const size_t nk = (size_t)fe->kpCap, fsz = (size_t)fe->cam.Iw * fe->cam.Ih;
+    if ((rc = fork_lanes(fe, nlanes))) return rc;
+    for (int ln = 0; ln < nlanes; ln++) {
+        const int f0 = (int)((long long)batch * ln / nlanes), f1 = (int)((long long)batch * (ln + 1) / nlanes), cnt = f1 - f0;
+        if (cnt <= 0) continue;
+        if ((rc = launch_warp(fe, fe->lane[ln], fisheye_dev + (size_t)f0 * fsz, f0, cnt))) return rc;
+        if ((rc = launch_extract(fe, fe->lane[ln], f0, cnt, kps_dev + (size_t)f0 * nk, desc_dev + (size_t)f0 * nk * 32, n_out_dev + f0, true))) return rc;
+    }
+    fe->lastBatch = batch;
+    return join_lanes(fe, nlanes);
 }
 
 extern "C" int cslam_frontend_level_size(const cslam_frontend* fe, int level, int* w, int* h) {
