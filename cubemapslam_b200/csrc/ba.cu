@@ -209,58 +209,58 @@ __global__ void __launch_bounds__(256) k_ba_schur(BADev D, int chunks) {
 // Dense LDL^T (no pivoting) + solve of the n x n reduced camera system in one CTA, blocked (panel NB) so that the O(n^3)
 // work reads the panel from shared memory. scal[3] = 1 on a zero / non-finite pivot (LinearSolverEigen's failure).
 static const int LD_NB = 32;
+// The right-hand side g is stored right behind S, i.e. it is row n of an (n+1) x n matrix: carrying it through the
+// factorisation as one more row below the panel performs the forward substitution for free (row n of L = D^-1 L^-1 g).
 __global__ void __launch_bounds__(1024) k_ba_solve(BADev D) {
-    extern __shared__ double sm[];   // panel: n x (NB+1), d: n, y: n
-    const int n = D.n, T = blockDim.x, tid = threadIdx.x;
-    double* A = D.S;                 // lower triangle used, overwritten by L (unit diagonal implied) ; symmetric input
-    double* P = sm; double* dvec = sm + (size_t)n * (LD_NB + 1); double* y = dvec + n;
+    extern __shared__ double sm[];   // panel L: (n+1) x (NB+1) ; panel L*d: same ; d: n ; x: n
+    const int n = D.n, T = blockDim.x, tid = threadIdx.x, PS = LD_NB + 1;
+    double* A = D.S;                 // (n+1) x n, lower triangle + row n used; overwritten by L (unit diagonal implied)
+    double* P = sm; double* PD = P + (size_t)(n + 1) * PS; double* dvec = PD + (size_t)(n + 1) * PS; double* y = dvec + n;
     __shared__ int fail;
     if (tid == 0) fail = 0;
     __syncthreads();
     for (int jb = 0; jb < n; jb += LD_NB) {
-        const int nb = min(LD_NB, n - jb), rows = n - jb;
-        for (int i = tid; i < rows * nb; i += T) { const int r = i / nb, c = i - r * nb; P[r * (LD_NB + 1) + c] = A[(size_t)(jb + r) * n + jb + c]; }
+        const int nb = min(LD_NB, n - jb), rows = n + 1 - jb;
+        for (int i = tid; i < rows * nb; i += T) { const int r = i / nb, c = i - r * nb; P[r * PS + c] = A[(size_t)(jb + r) * n + jb + c]; }
         __syncthreads();
         for (int c = 0; c < nb; c++) {
-            const double dc = P[c * (LD_NB + 1) + c];
+            const double dc = P[c * PS + c];
             if (tid == 0) { if (dc == 0.0 || !isfinite(dc)) fail = 1; dvec[jb + c] = dc; }
             __syncthreads();
             if (fail) break;
-            for (int r = c + 1 + tid; r < rows; r += T) P[r * (LD_NB + 1) + c] /= dc;
+            const double inv = 1.0 / dc;
+            for (int r = c + 1 + tid; r < rows; r += T) { const double v = P[r * PS + c]; PD[r * PS + c] = v; P[r * PS + c] = v * inv; }   // PD = L*d (the unscaled column)
             __syncthreads();
             // rank-1 update of the remaining panel columns c2 in (c, nb), rows r >= c2
             const int ncol = nb - c - 1;
             for (int i = tid; i < (rows - c - 1) * ncol; i += T) {
                 const int r = c + 1 + i / ncol, c2 = c + 1 + i % ncol;
-                if (r >= c2) P[r * (LD_NB + 1) + c2] -= P[r * (LD_NB + 1) + c] * dc * P[c2 * (LD_NB + 1) + c];
+                if (r >= c2) P[r * PS + c2] -= PD[r * PS + c] * P[c2 * PS + c];
             }
             __syncthreads();
         }
         if (fail) break;
-        // write L panel back, then trailing update A[i][k] -= sum_c L[i][c] d_c L[k][c] for i >= k >= jb+nb
-        for (int i = tid; i < rows * nb; i += T) { const int r = i / nb, c = i - r * nb; if (r > c) A[(size_t)(jb + r) * n + jb + c] = P[r * (LD_NB + 1) + c]; }
-        const int tr = rows - nb;
-        for (int i = tid; i < tr * tr; i += T) {
-            const int r = i / tr, k = i - r * tr;
-            if (k > r) continue;
-            const double* Lr = P + (size_t)(nb + r) * (LD_NB + 1);
-            const double* Lk = P + (size_t)(nb + k) * (LD_NB + 1);
-            double s = 0;
-            for (int c = 0; c < nb; c++) s += Lr[c] * dvec[jb + c] * Lk[c];
-            A[(size_t)(jb + nb + r) * n + jb + nb + k] -= s;
+        // write L panel back, then trailing update A[i][k] -= sum_c (L[i][c] d_c) L[k][c] for rows i >= cols k >= jb+nb
+        for (int i = tid; i < rows * nb; i += T) { const int r = i / nb, c = i - r * nb; if (r > c) A[(size_t)(jb + r) * n + jb + c] = P[r * PS + c]; }
+        const int trR = rows - nb, trC = n - jb - nb;      // rows include the rhs row, columns do not
+        const int halfC = (trC + 1) >> 1;
+        for (int i = tid; i < trR * halfC; i += T) {
+            const int r = i / halfC, k0 = 2 * (i - r * halfC), k1 = k0 + 1;
+            if (k0 > r) continue;
+            const double* Lr = PD + (size_t)(nb + r) * PS;
+            const double* Lk0 = P + (size_t)(nb + k0) * PS;
+            const double* Lk1 = P + (size_t)(nb + min(k1, trC - 1)) * PS;
+            double s0 = 0, s1 = 0;
+            for (int c = 0; c < nb; c++) { const double a = Lr[c]; s0 += a * Lk0[c]; s1 += a * Lk1[c]; }
+            double* dst = A + (size_t)(jb + nb + r) * n + jb + nb;
+            dst[k0] -= s0;
+            if (k1 <= r && k1 < trC) dst[k1] -= s1;
         }
         __syncthreads();
     }
     if (fail) { if (tid == 0) D.scal[3] = 1.0; return; }
-    // forward: L y = g ; then y /= d ; backward: L^T x = y. One warp per dot product, columns processed in order.
-    for (int i = tid; i < n; i += T) y[i] = D.g[i];
-    __syncthreads();
-    for (int j = 0; j < n; j++) {
-        const double yj = y[j];
-        for (int i = j + 1 + tid; i < n; i += T) y[i] -= A[(size_t)i * n + j] * yj;
-        __syncthreads();
-    }
-    for (int i = tid; i < n; i += T) y[i] /= dvec[i];
+    // backward: L^T x = z, z = row n of L (= D^-1 L^-1 g); rows of L are contiguous in A
+    for (int i = tid; i < n; i += T) y[i] = A[(size_t)n * n + i];
     __syncthreads();
     for (int j = n - 1; j >= 0; j--) {
         const double xj = y[j];
@@ -543,7 +543,7 @@ extern "C" int cslam_optimizer_create(cslam_optimizer** out, int device) {
         set_error("optimizer: stream / pinned allocation failed"); delete o; return CSLAM_E_CUDA;
     }
     cudaFuncSetAttribute(k_ba_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    cudaFuncSetAttribute(k_ba_schur, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+    cudaFuncSetAttribute(k_ba_schur, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     cudaFuncSetAttribute(k_ba_linearize, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
     *out = o;
     return CSLAM_OK;
@@ -683,12 +683,12 @@ struct BAHost {
             // Hpp / bp are already full sums on every rank: rank 0 alone seeds [S | g | bpr] with them, the others start from 0
             if (o->rank == 0) { k_ba_s_init<<<grid(D.n * D.n), 256, 0, o->stream>>>(D); o->launches++; }
             else CSLAM_CUDA(cudaMemsetAsync(D.S, 0, ((size_t)D.n * D.n + 2 * D.n) * 8, o->stream));
-            const int chunks = 8;
+            const int chunks = 16;
             k_ba_schur<<<dim3(chunks, D.nKF), 256, (size_t)(6 * D.n + 6) * 8, o->stream>>>(D, chunks); o->launches++;
             if ((rc = allreduce(D.S, (size_t)D.n * D.n + 2 * D.n, NCCL_SUM))) return rc;
             k_ba_add_lambda<<<grid(D.n), 256, 0, o->stream>>>(D, lambda); o->launches++;
             if ((rc = zero_scal(3, 1))) return rc;
-            const size_t smem = ((size_t)D.n * (LD_NB + 1) + 2 * D.n) * 8;
+            const size_t smem = (2 * (size_t)(D.n + 1) * (LD_NB + 1) + 2 * D.n) * 8;
             if (smem > 200 * 1024) { set_error("reduced camera system too large for the single-CTA solver (n=%d)", D.n); return CSLAM_E_CAPACITY; }
             k_ba_solve<<<1, 1024, smem, o->stream>>>(D); o->launches++;
         }
