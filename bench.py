@@ -205,6 +205,10 @@ def run_ours(args):
     e2e_value = world * ef * args.e2e_steps / float(te.item())
     h2d = ef * fsz; d2h = ef * (kp_cap * 60 + 4)
 
+    sharded = None
+    if world > 1 and not args.no_extra:
+        import bench_extra
+        sharded = bench_extra.run_sharded_ba(local, rank, world, dist, torch)
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -239,7 +243,9 @@ def run_ours(args):
     # ---- CPU baseline: the oracle port on the host cores, bounded sample of the same workload
     cpu = cpu_baseline(cfg, mask, base_host, args)
     extra = {}
-    if not args.no_extra:
+    if sharded is not None:
+        extra = {"local_ba_sharded": sharded}
+    elif not args.no_extra:
         import bench_extra
         fe.close()
         del fish, kps, desc

@@ -104,3 +104,26 @@ def run(args, local):
     except Exception as e:
         out["local_ba"] = {"error": repr(e)}
     return out
+
+
+def run_sharded_ba(local, rank, world, dist, torch):
+    """LocalBA config 4 with landmarks sharded over all ranks (NCCL all-reduce of the reduced camera system); all ranks call."""
+    from cubemapslam_b200.optimizer import Optimizer
+    p = synth.ba_problem()
+    a = (p["Tcw"], p["kf_fixed"], p["pts"], p["eMP"], p["eKF"], p["kpxy"], p["inv_sigma2"], 650, 650)
+    o = Optimizer(device=local)
+    idt = torch.zeros(128, dtype=torch.uint8, device="cuda")
+    if rank == 0:
+        idt.copy_(torch.from_numpy(Optimizer.nccl_unique_id()))
+    dist.broadcast(idt, 0)
+    o.init_nccl(idt.cpu().numpy(), rank, world)
+    o.LocalBundleAdjustment(*a, its1=1, its2=0)
+    torch.cuda.synchronize(); dist.barrier()
+    t0 = time.perf_counter()
+    g = o.LocalBundleAdjustment(*a)
+    torch.cuda.synchronize(); dist.barrier()
+    dt = time.perf_counter() - t0
+    tt = torch.tensor([dt], dtype=torch.float64, device="cuda"); dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    o.close()
+    return {"config": "configs[3] landmark-sharded over %d GPUs, NCCL all-reduce of [S|g] per LM trial" % world, "lm_iters": int(g["iters"]),
+            "seconds": round(float(tt.item()), 4), "lm_iters_per_s": round(g["iters"] / float(tt.item()), 2)}
