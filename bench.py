@@ -226,7 +226,16 @@ def run_ours(args):
             "k_describe": int(nkp * (43 * 43 + 31 * 31 + 60)), "k_distribute": None}
     dom = max(tm, key=lambda k: tm[k][0])
     hbm, tf, how = peaks()
-    roof = {"kernel": dom, "bound": "hbm", "peak": hbm, "peak_source": how, "unit": "GB/s", "traffic": None, "share_of_step": shares[dom], "kernel_shares": shares}
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tp):
+        tj = json.load(open(tp))
+        if dom in tj.get("dram_bytes_per_frame", {}):
+            traffic = int(tj["dram_bytes_per_frame"][dom] * B)       # per launch group of one batch, like `achieved`
+    roof = {"kernel": dom, "bound": "hbm", "peak": hbm, "peak_source": how, "unit": "GB/s", "traffic": traffic, "share_of_step": shares[dom], "kernel_shares": shares}
+    if dom == "k_fast":
+        roof["note"] = ("k_fast is ALU-pipe bound, not HBM bound: the exact FAST arc score costs ~60 integer instructions per pixel "
+                        "(ncu: ALU pipe 68 % active, DRAM 2-3 %); `frac` is reported against HBM as the contract asks")
     nbatches = min(frames, 4 * B) // B
     if algo.get(dom):
         # per launch: bytes of one batch; k_pyramid/k_fast are nlevels(-1) launches per batch -> use the per-batch total
@@ -311,7 +320,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--frames", type=int, default=4096)
-    ap.add_argument("--batch", type=int, default=64)
+    ap.add_argument("--batch", type=int, default=128)
     ap.add_argument("--e2e-frames", type=int, default=1024)
     ap.add_argument("--e2e-steps", type=int, default=2)
     ap.add_argument("--match-pairs", type=int, default=4096)

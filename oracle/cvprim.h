@@ -12,6 +12,7 @@
 //   cv::fastAtan2        src/ORBExtractor.cpp:74
 //   cvRound              src/ORBExtractor.cpp:52,86,90-91,414,432,933
 #pragma once
+#include <algorithm>
 #include <cfloat>
 #include <cmath>
 #include <cstdint>
@@ -120,18 +121,28 @@ static const int kRingDy[16] = {-3, -3, -2, -1, 0, 1, 2, 3, 3, 3, 2, 1, 0, -1, -
 // Arc score s: largest t such that 9 contiguous ring pixels are all > p+t-... i.e. the pixel is a
 // FAST corner for every threshold < s. corner(thr) <=> s > thr ; OpenCV response = s-1.
 static inline int fast_arc_score(const uint8_t* p, int stride) {
-    int d[25];
-    int c = p[0];
+    // max over the 16 arcs of 9 contiguous ring pixels of max(min(d), min(-d)); sliding min/max by doubling (2,4,8,+1)
+    int d[16];
+    const int c = p[0];
     for (int k = 0; k < 16; k++) d[k] = c - p[kRingDy[k] * stride + kRingDx[k]];
-    for (int k = 16; k < 25; k++) d[k] = d[k - 16];
+    int mn2[16], mx2[16], mn4[16], mx4[16];
+    for (int k = 0; k < 16; k++) { mn2[k] = std::min(d[k], d[(k + 1) & 15]); mx2[k] = std::max(d[k], d[(k + 1) & 15]); }
+    for (int k = 0; k < 16; k++) { mn4[k] = std::min(mn2[k], mn2[(k + 2) & 15]); mx4[k] = std::max(mx2[k], mx2[(k + 2) & 15]); }
     int best = 0;
     for (int k = 0; k < 16; k++) {
-        int mn = d[k], mx = d[k];
-        for (int j = 1; j < 9; j++) { int v = d[k + j]; if (v < mn) mn = v; if (v > mx) mx = v; }
-        if (mn > best) best = mn;
-        if (-mx > best) best = -mx;
+        const int a = std::min(std::min(mn4[k], mn4[(k + 4) & 15]), d[(k + 8) & 15]);
+        const int b = std::max(std::max(mx4[k], mx4[(k + 4) & 15]), d[(k + 8) & 15]);
+        best = std::max(best, std::max(a, -b));
     }
     return best;
+}
+// corner test at threshold thr (9 contiguous ring pixels all brighter or all darker by more than thr), bit masks
+static inline bool fast_is_corner(const uint8_t* p, int stride, int thr) {
+    const int c = p[0];
+    unsigned hi = 0, lo = 0;
+    for (int k = 0; k < 16; k++) { const int v = p[kRingDy[k] * stride + kRingDx[k]]; hi |= (unsigned)(v > c + thr) << k; lo |= (unsigned)(v < c - thr) << k; }
+    auto arc9 = [](unsigned m) { m |= m << 16; unsigned a = m & (m >> 1); a &= a >> 2; a &= a >> 4; a &= m >> 8; return (a & 0xffffu) != 0; };
+    return arc9(hi) || arc9(lo);
 }
 
 struct FastKp { int x, y, response; };
@@ -156,8 +167,8 @@ static inline void fast_nms(const uint8_t* img, int w, int h, int stride, int th
             if (in(p[3]) && in(p[-3])) continue;
             if (in(p[o2]) && in(p[o10])) continue;
             if (in(p[o6]) && in(p[o14])) continue;
-            int s = fast_arc_score(p, stride);
-            if (s > thr) sc[(size_t)y * w + x] = s - 1;
+            if (!fast_is_corner(p, stride, thr)) continue;
+            sc[(size_t)y * w + x] = fast_arc_score(p, stride) - 1;   // a corner at thr has score > thr
         }
     }
     for (int y = 3; y < h - 3; y++)
