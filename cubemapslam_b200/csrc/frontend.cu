@@ -213,6 +213,9 @@ __global__ void __launch_bounds__(256) k_fast(const uint8_t* __restrict__ img, L
     const int ncell = min(CG, g.nColsEff - j0);
     const int tx0 = g.minB + j0 * g.wCell, tx1 = min(tx0 + ncell * g.wCell + 6, g.maxBX);
     const int a0 = tx0 & ~3, nwords = (tx1 - a0 + 3) >> 2, nrows = maxY - iniY;
+    const int nx = tx1 - tx0 - 6, ny = nrows - 6;   // detection area
+    const int xoff = tx0 - a0 + 3;                   // tile column of detection x = 0
+    const int w0 = xoff >> 2, w1 = (xoff + nx + 3) >> 2, nw = w1 - w0;   // S/tile words covering the detection columns
     if (tid < CG) cnt20[tid] = 0;
     if (tid == 0) { anyNonZero = 0; nK = 0; }
     __syncthreads();
@@ -228,9 +231,6 @@ __global__ void __launch_bounds__(256) k_fast(const uint8_t* __restrict__ img, L
         }
     }
     if (acc) anyNonZero = 1;
-    const int nx = tx1 - tx0 - 6, ny = nrows - 6;   // detection area
-    const int xoff = tx0 - a0 + 3;                   // tile column of detection x = 0
-    const int w0 = xoff >> 2, w1 = (xoff + nx + 3) >> 2, nw = w1 - w0;   // S/tile words covering the detection columns
     // S2 must read 0 around the scored area: rows 0 and ny+1, and the pair-words left/right of [2*w0, 2*w1) in every row
     for (int i = tid; i < 2 * FAST_SW; i += 256) S2[(i >= FAST_SW ? (ny + 1) * FAST_SW : 0) + (i % FAST_SW)] = 0;
     for (int i = tid; i < 2 * ny; i += 256) {
@@ -658,7 +658,6 @@ static const int DH_STRIDE = 44;                 // transposed H: u16 per row in
 __global__ void __launch_bounds__(DESC_WARPS * 32) k_describe(DescribeArgs A) {
     __shared__ __align__(16) uint8_t s_patch[DESC_WARPS][43 * DP_STRIDE + 16];
     __shared__ __align__(16) uint16_t s_ht[DESC_WARPS][37 * DH_STRIDE + 8];
-    __shared__ __align__(16) uint8_t s_blur[DESC_WARPS][37 * 40];
     __shared__ signed char s_pat[1024];
     const int level = blockIdx.y, frame = blockIdx.z;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -736,7 +735,7 @@ __global__ void __launch_bounds__(DESC_WARPS * 32) k_describe(DescribeArgs A) {
     }
     __syncwarp();
     // Vertical: 4 output rows of one column per item from five u16x2 words with IDP.2A; dst = (V + 32768) >> 16
-    uint8_t* Bl = s_blur[warp];
+    uint8_t* Bl = s_patch[warp];   // the raw patch is dead after the horizontal pass
     {
         const uint32_t K01 = 18u | (34u << 8), K23 = 48u | (56u << 8), K45 = 48u | (34u << 8);
         for (int it = lane; it < 37 * 10; it += 32) {
