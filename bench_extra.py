@@ -56,8 +56,9 @@ def _match_leg(torch, dev, args, local):
     out["bruteforce"]["mean_matches"] = float(nm.float().mean().item()) if False else None
     # CPU oracle: bounded sample, all cores
     import oracle as orc
-    cores = os.cpu_count()
-    s = min(nb, max(4, cores // 8))
+    import bench as _b
+    cores = min(os.cpu_count() or 1, 2 * _b.host_cores())
+    s = nb
     hA = np.stack([b[0] for b in base[:s]]); haA = np.stack([b[1] for b in base[:s]]); hB = np.stack([b[2] for b in base[:s]]); haB = np.stack([b[3] for b in base[:s]])
     t0 = time.perf_counter()
     orc.match_bruteforce_batch(hA, haA, hB, haB, 0.6, 50, True, nthreads=min(cores, s))
