@@ -338,6 +338,7 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=2)
     ap.add_argument("--match-pairs", type=int, default=4096)
     ap.add_argument("--match-steps", type=int, default=2)
+    ap.add_argument("--pose-frames", type=int, default=2048)
     ap.add_argument("--no-extra", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":

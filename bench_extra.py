@@ -92,6 +92,31 @@ def _ba_leg(args, local):
     return out
 
 
+def _pose_leg(args, local):
+    """Batched Optimizer::PoseOptimization (config 5's pose-only BA stage): F independent frames x ~600 correspondences, host call."""
+    from cubemapslam_b200.optimizer import Optimizer
+    import oracle as orc
+    base = [synth.pose_problem(n=600, faceW=650, seed=100 + i, outlier_frac=0.1) for i in range(8)]
+    F = args.pose_frames
+    probs = [base[i % len(base)] for i in range(F)]
+    off = np.cumsum([0] + [len(q["Xw"]) for q in probs]).astype(np.int32)
+    T = np.stack([q["Tcw"] for q in probs]); Xw = np.concatenate([q["Xw"] for q in probs]); kp = np.concatenate([q["kpxy"] for q in probs])
+    w = np.concatenate([q["inv_sigma2"] for q in probs])
+    o = Optimizer(device=local)
+    o.PoseOptimization(T[:8], Xw[:off[8]], kp[:off[8]], w[:off[8]], 650, 650, offset=off[:9])
+    t0 = time.perf_counter()
+    g = o.PoseOptimization(T, Xw, kp, w, 650, 650, offset=off)
+    dt = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    r = [orc.pose_opt(q["Tcw"], q["Xw"], q["kpxy"], q["inv_sigma2"], 650, 650) for q in base]
+    dtc = time.perf_counter() - t0
+    ok = all(int(g["inliers"][i]) == r[i]["inliers"] for i in range(len(base)))
+    o.close()
+    return {"config": "configs[4] stage: PoseOptimization, %d frames x ~%d correspondences per host call" % (F, len(base[0]["Xw"])), "frames_per_s": round(F / dt, 1),
+            "seconds": round(dt, 4), "cpu_baseline": {"frames_per_s": round(len(base) / dtc, 1), "cores": 1, "kind": "port", "sample": "%d frames" % len(base)},
+            "inliers_equal_to_oracle": bool(ok)}
+
+
 def run(args, local):
     import torch
     dev = torch.device("cuda", local)
@@ -104,6 +129,10 @@ def run(args, local):
         out["local_ba"] = _ba_leg(args, local)
     except Exception as e:
         out["local_ba"] = {"error": repr(e)}
+    try:
+        out["pose_optimization"] = _pose_leg(args, local)
+    except Exception as e:
+        out["pose_optimization"] = {"error": repr(e)}
     return out
 
 

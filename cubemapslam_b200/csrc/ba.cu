@@ -209,11 +209,14 @@ __global__ void __launch_bounds__(256) k_ba_schur(BADev D, int chunks) {
 // Dense LDL^T (no pivoting) + solve of the n x n reduced camera system in one CTA, blocked (panel NB) so that the O(n^3)
 // work reads the panel from shared memory. scal[3] = 1 on a zero / non-finite pivot (LinearSolverEigen's failure).
 static const int LD_NB = 32;
-// The right-hand side g is stored right behind S, i.e. it is row n of an (n+1) x n matrix: carrying it through the
-// factorisation as one more row below the panel performs the forward substitution for free (row n of L = D^-1 L^-1 g).
+// Blocked right-looking LDL^T in one CTA. The right-hand side g is stored right behind S, i.e. it is row n of an (n+1) x n
+// matrix: carrying it through the factorisation as one more row performs the forward substitution for free (row n of L =
+// D^-1 L^-1 g). Per panel of NB columns: (1) warp 0 factors the NB x NB diagonal block with warp-level sync only,
+// (2) every row below is a NB-step forward substitution against it, one thread per row, no block syncs,
+// (3) trailing update with 4x2 register tiles from the shared-memory panel. Back substitution is blocked the same way.
 __global__ void __launch_bounds__(1024) k_ba_solve(BADev D) {
     extern __shared__ double sm[];   // panel L: (n+1) x (NB+1) ; panel L*d: same ; d: n ; x: n
-    const int n = D.n, T = blockDim.x, tid = threadIdx.x, PS = LD_NB + 1;
+    const int n = D.n, T = blockDim.x, tid = threadIdx.x, PS = LD_NB + 1, lane = tid & 31, warp = tid >> 5;
     double* A = D.S;                 // (n+1) x n, lower triangle + row n used; overwritten by L (unit diagonal implied)
     double* P = sm; double* PD = P + (size_t)(n + 1) * PS; double* dvec = PD + (size_t)(n + 1) * PS; double* y = dvec + n;
     __shared__ int fail;
@@ -223,48 +226,87 @@ __global__ void __launch_bounds__(1024) k_ba_solve(BADev D) {
         const int nb = min(LD_NB, n - jb), rows = n + 1 - jb;
         for (int i = tid; i < rows * nb; i += T) { const int r = i / nb, c = i - r * nb; P[r * PS + c] = A[(size_t)(jb + r) * n + jb + c]; }
         __syncthreads();
-        for (int c = 0; c < nb; c++) {
-            const double dc = P[c * PS + c];
-            if (tid == 0) { if (dc == 0.0 || !isfinite(dc)) fail = 1; dvec[jb + c] = dc; }
-            __syncthreads();
-            if (fail) break;
-            const double inv = 1.0 / dc;
-            for (int r = c + 1 + tid; r < rows; r += T) { const double v = P[r * PS + c]; PD[r * PS + c] = v; P[r * PS + c] = v * inv; }   // PD = L*d (the unscaled column)
-            __syncthreads();
-            // rank-1 update of the remaining panel columns c2 in (c, nb), rows r >= c2
-            const int ncol = nb - c - 1;
-            for (int i = tid; i < (rows - c - 1) * ncol; i += T) {
-                const int r = c + 1 + i / ncol, c2 = c + 1 + i % ncol;
-                if (r >= c2) P[r * PS + c2] -= PD[r * PS + c] * P[c2 * PS + c];
+        // (1) diagonal block: lane = row
+        if (warp == 0) {
+            for (int c = 0; c < nb; c++) {
+                const double dc = P[c * PS + c];
+                if (lane == 0) { if (dc == 0.0 || !isfinite(dc)) fail = 1; dvec[jb + c] = dc; }
+                if (lane > c && lane < nb) {
+                    const double v = P[lane * PS + c];
+                    PD[lane * PS + c] = v; P[lane * PS + c] = v / dc;
+                }
+                __syncwarp();
+                if (lane > c && lane < nb)
+                    for (int c2 = c + 1; c2 <= lane; c2++) P[lane * PS + c2] -= PD[lane * PS + c] * P[c2 * PS + c];
+                __syncwarp();
             }
-            __syncthreads();
         }
+        __syncthreads();
         if (fail) break;
-        // write L panel back, then trailing update A[i][k] -= sum_c (L[i][c] d_c) L[k][c] for rows i >= cols k >= jb+nb
+        // (2) rows below the diagonal block (including the rhs row): v_c = a_c - sum_{c'<c} (L d)[r][c'] L[c][c'] ; L[r][c] = v_c / d_c
+        for (int r = nb + tid; r < rows; r += T) {
+            double* Pr = P + (size_t)r * PS; double* PDr = PD + (size_t)r * PS;
+            for (int c = 0; c < nb; c++) {
+                double v = Pr[c];
+                const double* Lc = P + (size_t)c * PS;
+                for (int c2 = 0; c2 < c; c2++) v -= PDr[c2] * Lc[c2];
+                PDr[c] = v; Pr[c] = v / dvec[jb + c];
+            }
+        }
+        __syncthreads();
+        // write L panel back, then trailing update A[i][k] -= sum_c (L[i][c] d_c) L[k][c] for rows i >= cols k >= jb+nb, 4x2 tiles
         for (int i = tid; i < rows * nb; i += T) { const int r = i / nb, c = i - r * nb; if (r > c) A[(size_t)(jb + r) * n + jb + c] = P[r * PS + c]; }
         const int trR = rows - nb, trC = n - jb - nb;      // rows include the rhs row, columns do not
-        const int halfC = (trC + 1) >> 1;
-        for (int i = tid; i < trR * halfC; i += T) {
-            const int r = i / halfC, k0 = 2 * (i - r * halfC), k1 = k0 + 1;
-            if (k0 > r) continue;
-            const double* Lr = PD + (size_t)(nb + r) * PS;
-            const double* Lk0 = P + (size_t)(nb + k0) * PS;
-            const double* Lk1 = P + (size_t)(nb + min(k1, trC - 1)) * PS;
-            double s0 = 0, s1 = 0;
-            for (int c = 0; c < nb; c++) { const double a = Lr[c]; s0 += a * Lk0[c]; s1 += a * Lk1[c]; }
-            double* dst = A + (size_t)(jb + nb + r) * n + jb + nb;
-            dst[k0] -= s0;
-            if (k1 <= r && k1 < trC) dst[k1] -= s1;
+        const int tR = (trR + 3) >> 2, tC = (trC + 1) >> 1;
+        for (int i = tid; i < tR * tC; i += T) {
+            const int br = i / tC, bc = i - br * tC;
+            const int r0 = 4 * br, k0 = 2 * bc;
+            if (k0 > r0 + 3) continue;                      // tile entirely above the diagonal
+            const double* Lr[4]; const double* Lk[2];
+#pragma unroll
+            for (int a = 0; a < 4; a++) Lr[a] = PD + (size_t)(nb + min(r0 + a, trR - 1)) * PS;
+#pragma unroll
+            for (int bq = 0; bq < 2; bq++) Lk[bq] = P + (size_t)(nb + min(k0 + bq, trC - 1)) * PS;
+            double acc[4][2] = {{0, 0}, {0, 0}, {0, 0}, {0, 0}};
+            for (int c = 0; c < nb; c++) {
+                const double b0 = Lk[0][c], b1 = Lk[1][c];
+#pragma unroll
+                for (int a = 0; a < 4; a++) { const double av = Lr[a][c]; acc[a][0] += av * b0; acc[a][1] += av * b1; }
+            }
+#pragma unroll
+            for (int a = 0; a < 4; a++) {
+                const int r = r0 + a;
+                if (r >= trR) break;
+                double* dst = A + (size_t)(jb + nb + r) * n + jb + nb;
+                if (k0 <= r && k0 < trC) dst[k0] -= acc[a][0];
+                if (k0 + 1 <= r && k0 + 1 < trC) dst[k0 + 1] -= acc[a][1];
+            }
         }
         __syncthreads();
     }
     if (fail) { if (tid == 0) D.scal[3] = 1.0; return; }
-    // backward: L^T x = z, z = row n of L (= D^-1 L^-1 g); rows of L are contiguous in A
+    // backward: L^T x = z, z = row n of L (= D^-1 L^-1 g); processed in blocks of NB columns from the bottom
     for (int i = tid; i < n; i += T) y[i] = A[(size_t)n * n + i];
     __syncthreads();
-    for (int j = n - 1; j >= 0; j--) {
-        const double xj = y[j];
-        for (int i = tid; i < j; i += T) y[i] -= A[(size_t)j * n + i] * xj;
+    for (int je = n; je > 0; je -= LD_NB) {
+        const int j0 = max(je - LD_NB, 0), nb = je - j0;
+        // load the nb x nb diagonal block of L into P (row-major), solve it with warp 0: x_j final for j in [j0, je)
+        for (int i = tid; i < nb * nb; i += T) { const int r = i / nb, c = i - r * nb; P[r * PS + c] = (r > c) ? A[(size_t)(j0 + r) * n + j0 + c] : 0.0; }
+        __syncthreads();
+        if (warp == 0) {
+            for (int j = nb - 1; j >= 0; j--) {
+                const double xj = y[j0 + j];
+                if (lane < j) y[j0 + lane] -= P[j * PS + lane] * xj;
+                __syncwarp();
+            }
+        }
+        __syncthreads();
+        // rows above: y[i] -= sum_{j in block} L[j][i] x_j   (rows of L are contiguous: coalesced over i)
+        for (int i = tid; i < j0; i += T) {
+            double s = 0;
+            for (int j = 0; j < nb; j++) s += A[(size_t)(j0 + j) * n + i] * y[j0 + j];
+            y[i] -= s;
+        }
         __syncthreads();
     }
     for (int i = tid; i < n; i += T) D.xp[i] = y[i];
