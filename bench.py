@@ -294,7 +294,7 @@ def cpu_baseline(cfg, mask, base_frames, args, threads=None, nframes=None):
     cores = threads or min(os.cpu_count() or 1, 2 * quota)     # 2 worker threads per granted CPU measured fastest on the box
     cp = orc.cam_params(cfg)
     m1, m2 = orc.build_maps(cp)
-    n = nframes or max(cores, min(2 * cores, 256))
+    n = nframes or 20 * cores          # ~10 s of CPU work at the measured rate
     fr = np.stack([base_frames[i % len(base_frames)] for i in range(n)])
     orc.warp_extract_batch(cp, fr[:min(n, cores)], m1, m2, mask, 3000, 1.2, 8, 20, 7, cores)     # warm-up
     t0 = time.perf_counter()
@@ -314,7 +314,7 @@ def run_reference(args):
     base = np.stack([synth.fisheye_frame(cfg, i) for i in range(N_BASE)])
     vals = []
     for i in range(args.warmup + args.steps):
-        c = cpu_baseline(cfg, mask, base, args, nframes=128)
+        c = cpu_baseline(cfg, mask, base, args, nframes=256)
         if i >= args.warmup:
             vals.append(c)
     v = float(np.mean([c["value"] for c in vals]))
