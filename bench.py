@@ -30,7 +30,7 @@ N_BASE = 16          # distinct synthetic frames generated with the SURVEY §8d 
 
 def load_mask():
     import cv2
-    return cv2.imread(config.fixture("gray_cubemap_front_mask_650.png"), cv2.IMREAD_GRAYSCALE)
+    return config.load_mask("gray_cubemap_front_mask_650")
 
 
 def peaks():

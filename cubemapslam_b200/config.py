@@ -32,11 +32,30 @@ def fixture(name):
     return os.path.join(_FIXTURES, name)
 
 
+def camera(name, **overrides):
+    """Parameters of one of the reference's settings files (tests/fixtures/cameras.json holds the values of
+    Config/{lafida_cam0,front_cam,left_cam}_params.yaml under the reference's own key names)."""
+    import json
+    cfg = dict(json.load(open(fixture("cameras.json")))["cameras"][name])
+    for k, v in overrides.items():
+        cfg[k.replace("_", ".", 1)] = float(v)
+    return cfg
+
+
+def load_mask(name):
+    """Binary cubemap mask (0/255, uint8) shipped by the reference under Masks/<name>.png, stored bit-packed in
+    tests/fixtures/cubemap_masks.npz."""
+    import numpy as np
+    z = np.load(fixture("cubemap_masks.npz"))
+    h, w = (int(v) for v in z[name + "_shape"])
+    return (np.unpackbits(z[name + "_bits"])[:h * w].reshape(h, w) * 255).astype(np.uint8)
+
+
 def lafida_450():
     """BASELINE config 1: lafida_cam0_params.yaml with 450-px faces (mask gray_lafida_cubemap_mask_450.png)."""
-    return load_settings(fixture("lafida_cam0_params.yaml"), CubeFace_w=450, CubeFace_h=450)
+    return camera("lafida_cam0_params", CubeFace_w=450, CubeFace_h=450)
 
 
 def front_1024():
     """BASELINE configs 2/5: front_cam_params.yaml with a 1280x1024 synthetic sensor (Ih 1024, v0 512), 650-px faces."""
-    return load_settings(fixture("front_cam_params.yaml"), Camera_Ih=1024, Camera_v0=512.0)
+    return camera("front_cam_params", Camera_Ih=1024, Camera_v0=512.0)

@@ -24,7 +24,7 @@ def extract_golden():
     cp = orc.cam_params(cfg)
     m1, m2 = orc.build_maps(cp)
     canvas = orc.warp(cp, synth.fisheye_frame(cfg, 0), m1, m2)
-    mask = cv2.imread(config.fixture("gray_lafida_cubemap_mask_450.png"), cv2.IMREAD_GRAYSCALE)
+    mask = config.load_mask("gray_lafida_cubemap_mask_450")
     kps, desc = orc.ORBextractor(2000, 1.2, 8, 20, 7, 450, 450)(canvas, mask)
     np.savez_compressed(os.path.join(HERE, "extract_lafida450_frame0.npz"), kps=kps, desc=desc, canvas_sum=np.uint64(canvas.astype(np.uint64).sum()),
                         map_probe=np.stack([m1[::97, ::89], m2[::97, ::89]]))

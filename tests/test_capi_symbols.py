@@ -57,10 +57,17 @@ def test_product_never_imports_oracle():
     assert not offenders, offenders
 
 
-def test_settings_parser_matches_reference_yaml():
+def test_settings_fixture_and_parser(tmp_path):
     from cubemapslam_b200 import config
-    cfg = config.load_settings(config.fixture("lafida_cam0_params.yaml"))
+    cfg = config.camera("lafida_cam0_params")
     assert cfg["Camera.Iw"] == 754 and cfg["CubeFace.w"] == 650 and cfg["ORBextractor.nFeatures"] == 2000
     assert abs(cfg["Camera.pol11"] - 0.810799620714366) < 1e-15 and cfg["Camera.nrinvpol"] == 12
     f = config.front_1024()
     assert f["Camera.Ih"] == 1024 and f["Camera.v0"] == 512.0 and f["Camera.nrinvpol"] == 10
+    # the parser for the reference's "key: value" settings dialect (what a deployment would feed it)
+    p = tmp_path / "s.yaml"
+    p.write_text("%YAML:1.0\n# comment\nCamera.Iw: 754\nCamera.a2: 1.5e-03   # trailing\nViewer.Name: x\n")
+    y = config.load_settings(str(p), Camera_Iw=800)
+    assert y["Camera.Iw"] == 800 and y["Camera.a2"] == 1.5e-3 and y["Viewer.Name"] == "x"
+    m = config.load_mask("gray_lafida_cubemap_mask_450")
+    assert m.shape == (1350, 1350) and set(np.unique(m)) == {0, 255} and 0.29 < (m > 0).mean() < 0.31

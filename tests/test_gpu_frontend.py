@@ -16,7 +16,7 @@ def _fe(cfg, mask, **kw):
 @pytest.fixture(scope="module")
 def lafida(oracle):
     cfg = config.lafida_450()
-    mask = cv2.imread(config.fixture("gray_lafida_cubemap_mask_450.png"), cv2.IMREAD_GRAYSCALE)
+    mask = config.load_mask("gray_lafida_cubemap_mask_450")
     cp = oracle.cam_params(cfg)
     m1, m2 = oracle.build_maps(cp)
     fe = _fe(cfg, mask, max_batch=4)
@@ -92,7 +92,7 @@ def test_extract_host_canvas_and_full_mask(oracle, lafida):
 
 def test_config2_frame_650(oracle):
     cfg = config.front_1024()
-    mask = cv2.imread(config.fixture("gray_cubemap_front_mask_650.png"), cv2.IMREAD_GRAYSCALE)
+    mask = config.load_mask("gray_cubemap_front_mask_650")
     fe = _fe(cfg, mask, max_batch=2)
     cp = oracle.cam_params(cfg)
     m1, m2 = oracle.build_maps(cp)

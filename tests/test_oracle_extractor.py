@@ -18,7 +18,7 @@ def _canvas(oracle, cfg, idx):
 
 def test_stages_match_cv2_transcription(oracle):
     from tests.ref_cv2_extractor import extract_stages
-    cfg = config.load_settings(config.fixture("lafida_cam0_params.yaml"), CubeFace_w=150, CubeFace_h=150)
+    cfg = config.camera("lafida_cam0_params", CubeFace_w=150, CubeFace_h=150)
     cp, canvas, _ = _canvas(oracle, cfg, 3)
     assert canvas.shape == (450, 450)
     ex = oracle.ORBextractor(500, 1.2, 8, 20, 7, 150, 150)
@@ -47,7 +47,7 @@ def test_stages_match_cv2_transcription(oracle):
 def test_cull_and_scaling(oracle):
     cfg = config.lafida_450()
     cp, canvas, _ = _canvas(oracle, cfg, 0)
-    mask = cv2.imread(config.fixture("gray_lafida_cubemap_mask_450.png"), cv2.IMREAD_GRAYSCALE)
+    mask = config.load_mask("gray_lafida_cubemap_mask_450")
     assert mask.shape == canvas.shape == (1350, 1350)
     ex = oracle.ORBextractor(2000, 1.2, 8, 20, 7, 450, 450)
     kps, desc = ex(canvas, mask)
@@ -68,7 +68,7 @@ def test_golden_config1(oracle):
     g = np.load(path)
     cfg = config.lafida_450()
     cp, canvas, _ = _canvas(oracle, cfg, 0)
-    mask = cv2.imread(config.fixture("gray_lafida_cubemap_mask_450.png"), cv2.IMREAD_GRAYSCALE)
+    mask = config.load_mask("gray_lafida_cubemap_mask_450")
     kps, desc = oracle.ORBextractor(2000, 1.2, 8, 20, 7, 450, 450)(canvas, mask)
     assert np.array_equal(kps.view(np.uint8), g["kps"].view(np.uint8)) and np.array_equal(desc, g["desc"])
     assert int(canvas.astype(np.uint64).sum()) == int(g["canvas_sum"])

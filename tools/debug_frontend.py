@@ -4,7 +4,7 @@ import numpy as np, cv2
 import oracle as orc
 from cubemapslam_b200 import config, synth
 from cubemapslam_b200.frontend import FrontEnd
-cfg = config.lafida_450(); mask = cv2.imread(config.fixture("gray_lafida_cubemap_mask_450.png"), 0)
+cfg = config.lafida_450(); mask = config.load_mask("gray_lafida_cubemap_mask_450")
 cp = orc.cam_params(cfg); m1, m2 = orc.build_maps(cp)
 fe = FrontEnd(cfg, mask, max_batch=2)
 frame = synth.fisheye_frame(cfg, 0)

@@ -7,7 +7,7 @@ from cubemapslam_b200.frontend import FrontEnd
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 16
 reps = int(sys.argv[2]) if len(sys.argv) > 2 else 2
 cfg = config.front_1024()
-mask = cv2.imread(config.fixture("gray_cubemap_front_mask_650.png"), 0)
+mask = config.load_mask("gray_cubemap_front_mask_650")
 fe = FrontEnd(cfg, mask, max_batch=B)
 frames = np.stack([synth.fisheye_frame(cfg, i % 4) for i in range(B)])
 for _ in range(reps):
