@@ -134,7 +134,11 @@ __global__ void __launch_bounds__(BOW_THREADS) k_search_by_bow(const uint8_t* __
                                                                const uint8_t* __restrict__ kfValid, const int32_t* __restrict__ nodeKF, int nKF,
                                                                const uint8_t* __restrict__ descF, const float* __restrict__ angF,
                                                                const int32_t* __restrict__ nodeF, int nF, int n2K, int n2F, float nnratio, int checkOri,
-                                                               int32_t* __restrict__ matchF, int32_t* __restrict__ nmatches) {
+                                                               int32_t* __restrict__ matchF, int32_t* __restrict__ nmatches,
+                                                               const uint8_t* __restrict__ fValid, int kfkfMode) {
+    // kfkfMode = 0: SearchByBoW(KeyFrame*, Frame&)  (src/ORBMatcher.cpp:409-539), output per F feature.
+    // kfkfMode = 1: SearchByBoW(KeyFrame*, KeyFrame*) (:541-674): F-side features need fValid, acceptance is strict (< TH_LOW),
+    //               output per KF feature (index of the matched feature of the second key frame).
     extern __shared__ __align__(16) uint8_t smem[];
     uint32_t* keyKF = reinterpret_cast<uint32_t*>(smem);
     uint32_t* keyF = keyKF + n2K;
@@ -183,6 +187,7 @@ __global__ void __launch_bounds__(BOW_THREADS) k_search_by_bow(const uint8_t* __
             for (int p = fs + lane; p < fe; p += 32) {
                 const int iF = keyF[p] & 0xfff;
                 if (mF[iF] >= 0) continue;
+                if (kfkfMode && !fValid[(size_t)pair * nF + iF]) continue;
                 const int d = hamming256(a, __ldg(F4 + 2 * iF), __ldg(F4 + 2 * iF + 1));
                 if (d < best1) { best2 = best1; best1 = d; bpos = p; }
                 else if (d < best2) best2 = d;
@@ -195,7 +200,7 @@ __global__ void __launch_bounds__(BOW_THREADS) k_search_by_bow(const uint8_t* __
                 if (otherWins) { best2 = min(best1, ob2); best1 = ob1; bpos = op; }
                 else best2 = min(best2, ob1);
             }
-            if (best1 <= 50 && (float)best1 < __fmul_rn(nnratio, (float)best2)) {
+            if ((kfkfMode ? best1 < 50 : best1 <= 50) && (float)best1 < __fmul_rn(nnratio, (float)best2)) {
                 const int iF = keyF[bpos] & 0xfff;
                 if (lane == 0) {
                     mF[iF] = iK;
@@ -216,8 +221,15 @@ __global__ void __launch_bounds__(BOW_THREADS) k_search_by_bow(const uint8_t* __
         }
         __syncthreads();
     }
-    int32_t* out = matchF + (size_t)pair * nF;
-    for (int j = tid; j < nF; j += BOW_THREADS) out[j] = mF[j];
+    if (!kfkfMode) {
+        int32_t* out = matchF + (size_t)pair * nF;
+        for (int j = tid; j < nF; j += BOW_THREADS) out[j] = mF[j];
+    } else {
+        int32_t* out = matchF + (size_t)pair * nKF;
+        for (int i = tid; i < nKF; i += BOW_THREADS) out[i] = -1;
+        __syncthreads();
+        for (int j = tid; j < nF; j += BOW_THREADS) if (mF[j] >= 0) out[mF[j]] = j;
+    }
     if (tid == 0) nmatches[pair] = total;
 }
 
@@ -337,7 +349,7 @@ extern "C" int cslam_search_by_bow_dev(cslam_matcher* m, const uint8_t* descKF, 
     }
     const int n2K = pow2_at_least(nKF), n2F = pow2_at_least(nF);
     const size_t smem = (size_t)(n2K + n2F + nF) * 4;
-    k_search_by_bow<<<npairs, BOW_THREADS, smem, m->stream>>>(descKF, angKF, kf_valid, node_kf, nKF, descF, angF, node_f, nF, n2K, n2F, nnratio, check_ori, match_f, nmatches);
+    k_search_by_bow<<<npairs, BOW_THREADS, smem, m->stream>>>(descKF, angKF, kf_valid, node_kf, nKF, descF, angF, node_f, nF, n2K, n2F, nnratio, check_ori, match_f, nmatches, nullptr, 0);
     m->launches++;
     CSLAM_CUDA(cudaGetLastError());
     return CSLAM_OK;
@@ -374,6 +386,32 @@ extern "C" int cslam_hamming(cslam_matcher* m, const uint8_t* a, const uint8_t* 
     k_hamming<<<cdiv(n, 256), 256, 0, m->stream>>>(m->dA, m->dB, n, m->dDist);
     m->launches++;
     CSLAM_CUDA(cudaMemcpyAsync(dist, m->dDist, (size_t)n * 4, cudaMemcpyDeviceToHost, m->stream));
+    CSLAM_CUDA(cudaStreamSynchronize(m->stream));
+    return CSLAM_OK;
+}
+
+// ORBMatcher::SearchByBoW(KeyFrame*, KeyFrame*, vector<MapPoint*>&)  (reference src/ORBMatcher.cpp:541-674), host buffers.
+extern "C" int cslam_search_by_bow_kf(cslam_matcher* m, const uint8_t* desc1, const float* ang1, const uint8_t* valid1, const int32_t* node1, int n1,
+                                      const uint8_t* desc2, const float* ang2, const uint8_t* valid2, const int32_t* node2, int n2, int npairs, float nnratio,
+                                      int check_ori, int32_t* match12, int32_t* nmatches) {
+    int rc = check_sizes(m, n1, n2, npairs);
+    if (rc) return rc;
+    if (n1 == 0 || n2 == 0) { for (size_t i = 0; i < (size_t)npairs * n1; i++) match12[i] = -1; for (int p = 0; p < npairs; p++) nmatches[p] = 0; return CSLAM_OK; }
+    const size_t k1 = (size_t)npairs * n1, k2 = (size_t)npairs * n2;
+    CSLAM_CUDA(cudaMemcpyAsync(m->dA, desc1, k1 * 32, cudaMemcpyHostToDevice, m->stream)); CSLAM_CUDA(cudaMemcpyAsync(m->aA, ang1, k1 * 4, cudaMemcpyHostToDevice, m->stream));
+    CSLAM_CUDA(cudaMemcpyAsync(m->dValid, valid1, k1, cudaMemcpyHostToDevice, m->stream)); CSLAM_CUDA(cudaMemcpyAsync(m->nodeA, node1, k1 * 4, cudaMemcpyHostToDevice, m->stream));
+    CSLAM_CUDA(cudaMemcpyAsync(m->dB, desc2, k2 * 32, cudaMemcpyHostToDevice, m->stream)); CSLAM_CUDA(cudaMemcpyAsync(m->aB, ang2, k2 * 4, cudaMemcpyHostToDevice, m->stream));
+    CSLAM_CUDA(cudaMemcpyAsync(m->nodeB, node2, k2 * 4, cudaMemcpyHostToDevice, m->stream));
+    uint8_t* dValid2 = reinterpret_cast<uint8_t*>(m->dSecond);   // scratch: second12 is unused by this entry point
+    CSLAM_CUDA(cudaMemcpyAsync(dValid2, valid2, k2, cudaMemcpyHostToDevice, m->stream));
+    const int n2K = pow2_at_least(n1), n2F = pow2_at_least(n2);
+    const size_t smem = (size_t)(n2K + n2F + n2) * 4;
+    k_search_by_bow<<<npairs, BOW_THREADS, smem, m->stream>>>(m->dA, m->aA, m->dValid, m->nodeA, n1, m->dB, m->aB, m->nodeB, n2, n2K, n2F, nnratio, check_ori, m->dMatch, m->dN,
+                                                              dValid2, 1);
+    m->launches++;
+    CSLAM_CUDA(cudaGetLastError());
+    CSLAM_CUDA(cudaMemcpyAsync(match12, m->dMatch, k1 * 4, cudaMemcpyDeviceToHost, m->stream));
+    CSLAM_CUDA(cudaMemcpyAsync(nmatches, m->dN, (size_t)npairs * 4, cudaMemcpyDeviceToHost, m->stream));
     CSLAM_CUDA(cudaStreamSynchronize(m->stream));
     return CSLAM_OK;
 }

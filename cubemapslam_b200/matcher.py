@@ -85,6 +85,19 @@ class ORBMatcher:
                                         C.c_float(self.nnratio), int(self.check_ori), ptr(mf), ptr(n)))
         return (int(n[0]), mf[0]) if single else (n, mf)
 
+    def SearchByBoW_KF(self, desc1, ang1, valid1, node1, desc2, ang2, valid2, node2):
+        """SearchByBoW(KeyFrame*, KeyFrame*, ...) (reference src/ORBMatcher.cpp:541-674); match12 per feature of key frame 1."""
+        a = [np.ascontiguousarray(desc1, np.uint8), np.ascontiguousarray(ang1, np.float32), np.ascontiguousarray(valid1, np.uint8), np.ascontiguousarray(node1, np.int32),
+             np.ascontiguousarray(desc2, np.uint8), np.ascontiguousarray(ang2, np.float32), np.ascontiguousarray(valid2, np.uint8), np.ascontiguousarray(node2, np.int32)]
+        single = a[0].ndim == 2
+        if single:
+            a = [x[None] for x in a]
+        P, n1, n2 = a[0].shape[0], a[0].shape[1], a[4].shape[1]
+        m12 = np.empty((P, n1), np.int32); n = np.empty(P, np.int32)
+        check(lib().cslam_search_by_bow_kf(self._h, ptr(a[0]), ptr(a[1]), ptr(a[2]), ptr(a[3]), n1, ptr(a[4]), ptr(a[5]), ptr(a[6]), ptr(a[7]), n2, P,
+                                           C.c_float(self.nnratio), int(self.check_ori), ptr(m12), ptr(n)))
+        return (int(n[0]), m12[0]) if single else (n, m12)
+
     def search_by_bow_dev(self, descKF, angKF, kf_valid, node_kf, nKF, descF, angF, node_f, nF, npairs, match_f, nmatches):
         check(lib().cslam_search_by_bow_dev(self._h, ptr(descKF), ptr(angKF), ptr(kf_valid), ptr(node_kf), int(nKF), ptr(descF), ptr(angF), ptr(node_f),
                                             int(nF), int(npairs), C.c_float(self.nnratio), int(self.check_ori), ptr(match_f), ptr(nmatches)))

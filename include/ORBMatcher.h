@@ -46,6 +46,27 @@ public:
         return n;
     }
 
+    // Search matches between the MapPoints of two key frames, by vocabulary node (reference :541-674, used by loop closing)
+    template <class KeyFrameT, class MapPointT>
+    int SearchByBoW(KeyFrameT* pKF1, KeyFrameT* pKF2, std::vector<MapPointT*>& vpMatches12) {
+        const std::vector<MapPointT*> mp1 = pKF1->GetMapPointMatches(), mp2 = pKF2->GetMapPointMatches();
+        const int n1 = (int)mp1.size(), n2 = (int)mp2.size();
+        vpMatches12 = std::vector<MapPointT*>(n1, static_cast<MapPointT*>(NULL));
+        std::vector<uint8_t> d1((size_t)n1 * 32), d2((size_t)n2 * 32), v1(n1), v2(n2);
+        std::vector<float> a1(n1), a2(n2); std::vector<int32_t> nd1(n1, 0x7ffff), nd2(n2, 0x7fffe), m12(n1);
+        for (int i = 0; i < n1; i++) { std::memcpy(&d1[(size_t)i * 32], pKF1->mDescriptors.template ptr<unsigned char>(i), 32); a1[i] = pKF1->mvKeys[i].angle; v1[i] = mp1[i] && !mp1[i]->isBad(); }
+        for (int i = 0; i < n2; i++) { std::memcpy(&d2[(size_t)i * 32], pKF2->mDescriptors.template ptr<unsigned char>(i), 32); a2[i] = pKF2->mvKeys[i].angle; v2[i] = mp2[i] && !mp2[i]->isBad(); }
+        for (typename decltype(pKF1->mFeatVec)::const_iterator it = pKF1->mFeatVec.begin(); it != pKF1->mFeatVec.end(); ++it)
+            for (size_t k = 0; k < it->second.size(); k++) nd1[it->second[k]] = (int32_t)it->first;
+        for (typename decltype(pKF2->mFeatVec)::const_iterator it = pKF2->mFeatVec.begin(); it != pKF2->mFeatVec.end(); ++it)
+            for (size_t k = 0; k < it->second.size(); k++) nd2[it->second[k]] = (int32_t)it->first;
+        int32_t n = 0;
+        if (cslam_search_by_bow_kf(handle(), d1.data(), a1.data(), v1.data(), nd1.data(), n1, d2.data(), a2.data(), v2.data(), nd2.data(), n2, 1, mfNNratio,
+                                   mbCheckOrientation, m12.data(), &n) != CSLAM_OK) fatal();
+        for (int i = 0; i < n1; i++) if (m12[i] >= 0) vpMatches12[i] = mp2[m12[i]];
+        return n;
+    }
+
     static const int TH_LOW = 50;
     static const int TH_HIGH = 100;
     static const int HISTO_LENGTH = 12;

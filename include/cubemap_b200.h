@@ -122,6 +122,13 @@ int cslam_search_by_bow_dev(cslam_matcher* m, const uint8_t* descKF, const float
                             const int32_t* node_kf, int nKF, const uint8_t* descF, const float* angF, const int32_t* node_f,
                             int nF, int npairs, float nnratio, int check_ori, int32_t* match_f, int32_t* nmatches);
 
+/* ORBMatcher::SearchByBoW(KeyFrame*, KeyFrame*, vector<MapPoint*>&) (src/ORBMatcher.cpp:541-674, loop closing): both sides need a good
+ * MapPoint (valid1/valid2), features of the second key frame are consumed, acceptance is the strict best < TH_LOW.
+ * match12: npairs x n1 (index of the matched feature of key frame 2, or -1). */
+int cslam_search_by_bow_kf(cslam_matcher* m, const uint8_t* desc1, const float* ang1, const uint8_t* valid1, const int32_t* node1, int n1,
+                           const uint8_t* desc2, const float* ang2, const uint8_t* valid2, const int32_t* node2, int n2, int npairs,
+                           float nnratio, int check_ori, int32_t* match12, int32_t* nmatches);
+
 /* ---------------------------------------------------------------------------------------------- optimizer
  * Optimizer::LocalBundleAdjustment (src/Optimizer.cpp:192-451) on the already collected local window.
  * Vertices must be ordered like g2o orders them: KFs by mnId, points by mnId. */

@@ -94,6 +94,10 @@ int orc_search_by_bow(const uint8_t* descKF, const float* angKF, const uint8_t* 
                       const float* angF, const int* nodeF, int nF, float nnratio, int checkOri, int* matchF) {
     return search_by_bow(descKF, angKF, kfValid, nodeKF, nKF, descF, angF, nodeF, nF, nnratio, checkOri != 0, matchF);
 }
+int orc_search_by_bow_kf(const uint8_t* d1, const float* a1, const uint8_t* v1, const int* nd1, int n1, const uint8_t* d2, const float* a2, const uint8_t* v2,
+                         const int* nd2, int n2, float nnratio, int checkOri, int* match12) {
+    return search_by_bow_kf(d1, a1, v1, nd1, n1, d2, a2, v2, nd2, n2, nnratio, checkOri != 0, match12);
+}
 int orc_match_bruteforce(const uint8_t* descA, const float* angA, int nA, const uint8_t* descB, const float* angB, int nB, float nnratio,
                          int thLow, int checkOri, int* match12, int* dist12, int* second12) {
     return match_bruteforce(descA, angA, nA, descB, angB, nB, nnratio, thLow, checkOri != 0, match12, dist12, second12);

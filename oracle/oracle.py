@@ -189,6 +189,15 @@ def search_by_bow(descKF, angKF, kfValid, nodeKF, descF, angF, nodeF, nnratio=0.
     return n, matchF
 
 
+def search_by_bow_kf(desc1, ang1, valid1, node1, desc2, ang2, valid2, node2, nnratio=0.75, checkOri=True):
+    desc1 = _u8(desc1); desc2 = _u8(desc2); ang1 = _f32(ang1); ang2 = _f32(ang2)
+    valid1 = _u8(valid1); valid2 = _u8(valid2); node1 = _i32(node1); node2 = _i32(node2)
+    m = np.empty(desc1.shape[0], np.int32)
+    n = lib().orc_search_by_bow_kf(_p(desc1), _p(ang1), _p(valid1), _p(node1), desc1.shape[0], _p(desc2), _p(ang2), _p(valid2), _p(node2), desc2.shape[0],
+                                   C.c_float(nnratio), int(checkOri), _p(m))
+    return n, m
+
+
 def match_bruteforce(descA, angA, descB, angB, nnratio=0.6, thLow=50, checkOri=True):
     descA = _u8(descA); descB = _u8(descB); angA = _f32(angA); angB = _f32(angB)
     nA = descA.shape[0]

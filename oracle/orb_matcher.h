@@ -110,6 +110,53 @@ static inline int search_by_bow(const uint8_t* descKF, const float* angKF, const
     return nmatches;
 }
 
+// SearchByBoW(KeyFrame*, KeyFrame*, vector<MapPoint*>&)  (src/ORBMatcher.cpp:541-674): both sides need a good MapPoint, features of
+// KF2 are consumed (vbMatched2), acceptance is the STRICT bestDist1 < TH_LOW. match12[i] = index of the KF2 feature or -1.
+static inline int search_by_bow_kf(const uint8_t* desc1, const float* ang1, const uint8_t* valid1, const int* node1, int n1, const uint8_t* desc2,
+                                   const float* ang2, const uint8_t* valid2, const int* node2, int n2, float nnratio, bool checkOri, int* match12) {
+    std::map<int, std::vector<unsigned>> fv1, fv2;
+    for (int i = 0; i < n1; i++) fv1[node1[i]].push_back(i);
+    for (int i = 0; i < n2; i++) fv2[node2[i]].push_back(i);
+    for (int i = 0; i < n1; i++) match12[i] = -1;
+    std::vector<bool> vbMatched2(n2, false);
+    int nmatches = 0;
+    const int nBinsAngle = (int)std::ceil(360.0f / HISTO_LENGTH);
+    std::vector<std::vector<int>> rotHist(nBinsAngle);
+    auto f1it = fv1.begin(), f1end = fv1.end(); auto f2it = fv2.begin(), f2end = fv2.end();
+    while (f1it != f1end && f2it != f2end) {
+        if (f1it->first == f2it->first) {
+            for (size_t i1 = 0; i1 < f1it->second.size(); i1++) {
+                const size_t idx1 = f1it->second[i1];
+                if (!valid1[idx1]) continue;
+                int bestDist1 = 256, bestIdx2 = -1, bestDist2 = 256;
+                for (size_t i2 = 0; i2 < f2it->second.size(); i2++) {
+                    const size_t idx2 = f2it->second[i2];
+                    if (vbMatched2[idx2] || !valid2[idx2]) continue;
+                    const int dist = descriptor_distance(desc1 + 32 * idx1, desc2 + 32 * idx2);
+                    if (dist < bestDist1) { bestDist2 = bestDist1; bestDist1 = dist; bestIdx2 = (int)idx2; }
+                    else if (dist < bestDist2) bestDist2 = dist;
+                }
+                if (bestDist1 < TH_LOW && static_cast<float>(bestDist1) < nnratio * static_cast<float>(bestDist2)) {
+                    match12[idx1] = bestIdx2; vbMatched2[bestIdx2] = true;
+                    if (checkOri) rotHist[rot_bin(ang1[idx1], ang2[bestIdx2], nBinsAngle)].push_back((int)idx1);
+                    nmatches++;
+                }
+            }
+            f1it++; f2it++;
+        } else if (f1it->first < f2it->first) f1it = fv1.lower_bound(f2it->first);
+        else f2it = fv2.lower_bound(f1it->first);
+    }
+    if (checkOri) {
+        int ind1 = -1, ind2 = -1, ind3 = -1;
+        compute_three_maxima(rotHist.data(), nBinsAngle, ind1, ind2, ind3);
+        for (int i = 0; i < nBinsAngle; i++) {
+            if (i == ind1 || i == ind2 || i == ind3) continue;
+            for (size_t j = 0; j < rotHist[i].size(); j++) { match12[rotHist[i][j]] = -1; nmatches--; }
+        }
+    }
+    return nmatches;
+}
+
 // All-pairs matcher (defined above). match12[i] = column of B or -1; dist12[i] = best distance of row i
 // (always reported, also for rejected rows); second12[i] = second-best distance.
 static inline int match_bruteforce(const uint8_t* descA, const float* angA, int nA, const uint8_t* descB, const float* angB,

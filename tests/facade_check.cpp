@@ -28,7 +28,7 @@ struct Map { std::mutex mMutexMapUpdate; };
 struct Cam { float GetCosFovTh() { return -0.087f; } int GetCubeFaceWidth() { return 650; } int GetCubeFaceHeight() { return 650; } };
 int facade_check() {
     ORBextractor ex(2000, 1.2f, 8, 20, 7); cv::Mat im, mask, desc; std::vector<cv::KeyPoint> kps; ex(im, mask, kps, desc);
-    ORBMatcher m(0.7f, true); Frame F; KeyFrame K; std::vector<MapPoint*> out; int n = m.SearchByBoW(&K, F, out); n += ORBMatcher::DescriptorDistance(desc, desc);
+    ORBMatcher m(0.7f, true); Frame F; KeyFrame K; std::vector<MapPoint*> out; int n = m.SearchByBoW(&K, F, out); KeyFrame K2; n += m.SearchByBoW(&K, &K2, out); n += ORBMatcher::DescriptorDistance(desc, desc);
     Cam cam; Map map; bool stop = false; n += Optimizer::PoseOptimization(&F, &cam); Optimizer::LocalBundleAdjustment(&K, &stop, &map, &cam);
     return n + ex.GetLevels();
 }

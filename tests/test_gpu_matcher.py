@@ -90,3 +90,19 @@ def test_full_size_properties(matcher):
     mutual = sum(1 for i in range(2000) if m1[i] >= 0 and m2[m1[i]] == i)
     assert mutual > 0.95 * min(n1, n2)
     assert np.all(d1 <= s1) and np.all(d1[m1 >= 0] <= 50)
+
+
+def test_search_by_bow_keyframe_pair(oracle):
+    from cubemapslam_b200.matcher import ORBMatcher
+    rng = np.random.default_rng(12)
+    n = 1500
+    A, aA, B, aB, perm = synth.descriptor_pair(30, n=n)
+    node1 = rng.integers(0, 80, n).astype(np.int32); node2 = node1[perm].copy()
+    node2[rng.random(n) < 0.1] = 200
+    v1 = (rng.random(n) < 0.8).astype(np.uint8); v2 = (rng.random(n) < 0.8).astype(np.uint8)
+    m = ORBMatcher(0.75, True, max_pairs=2, max_features=2048)
+    got_n, got = m.SearchByBoW_KF(A, aA, v1, node1, B, aB, v2, node2)
+    ref_n, ref = oracle.search_by_bow_kf(A, aA, v1, node1, B, aB, v2, node2, 0.75, True)
+    assert got_n == ref_n and np.array_equal(got, ref) and ref_n > 200
+    assert np.all(v2[got[got >= 0]] == 1) and np.all(v1[got >= 0] == 1)
+    m.close()

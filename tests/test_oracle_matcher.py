@@ -136,3 +136,17 @@ def test_golden_match(oracle):
     assert n == int(g["bf_n"]) and np.array_equal(m, g["bf_match"]) and np.array_equal(d, g["bf_dist"]) and np.array_equal(s, g["bf_second"])
     nb, mf = oracle.search_by_bow(A, angA, g["valid"], g["nodeA"], B, angB, g["nodeB"], 0.7, True)
     assert nb == int(g["bow_n"]) and np.array_equal(mf, g["bow_match"])
+
+
+def test_bow_keyframe_pair_properties(oracle):
+    rng = np.random.default_rng(3)
+    A, angA, B, angB, perm = synth.descriptor_pair(5, n=400)
+    node1 = rng.integers(0, 30, 400).astype(np.int32); node2 = node1[perm].copy()
+    v1 = (rng.random(400) < 0.8).astype(np.uint8); v2 = (rng.random(400) < 0.8).astype(np.uint8)
+    n, m = oracle.search_by_bow_kf(A, angA, v1, node1, B, angB, v2, node2, 0.75, True)
+    ok = m >= 0
+    assert n == int(ok.sum()) and n > 50
+    assert np.all(v1[ok] == 1) and np.all(v2[m[ok]] == 1)                     # both sides need a good MapPoint
+    assert len(set(m[ok].tolist())) == n                                        # features of KF2 are consumed once
+    assert np.all(node1[ok] == node2[m[ok]])                                    # same vocabulary node
+    assert all(int(POP[A[i] ^ B[m[i]]].sum()) < 50 for i in np.nonzero(ok)[0])  # strict TH_LOW
