@@ -216,6 +216,7 @@ __global__ void __launch_bounds__(256) k_fast(const uint8_t* __restrict__ img, L
     const int nx = tx1 - tx0 - 6, ny = nrows - 6;   // detection area
     const int xoff = tx0 - a0 + 3;                   // tile column of detection x = 0
     const int w0 = xoff >> 2, w1 = (xoff + nx + 3) >> 2, nw = w1 - w0;   // S/tile words covering the detection columns
+    if (nx <= 0 || ny <= 0) return;   // block-uniform: a ROI with fewer than 7 rows / columns has no detection area (cv::FAST returns nothing)
     if (tid < CG) cnt20[tid] = 0;
     if (tid == 0) { anyNonZero = 0; nK = 0; }
     __syncthreads();
@@ -255,7 +256,7 @@ __global__ void __launch_bounds__(256) k_fast(const uint8_t* __restrict__ img, L
         cellInfo[x] = (uint8_t)(c | (xl == 0 ? 0x40 : 0) | ((xl == g.wCell - 1 || x == nx - 1) ? 0x80 : 0));
     }
     __syncthreads();
-    if (!anyNonZero || nx <= 0 || ny <= 0) return;   // an all-zero tile has no corners at any threshold
+    if (!anyNonZero) return;   // an all-zero tile has no corners at any threshold
     // ---- A
     const uint32_t mgw = fdiv_magic(nw);
     {

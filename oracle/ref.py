@@ -1,0 +1,117 @@
+"""ctypes wrapper around oracle/_ref/libref.so = the reference's own sources compiled unmodified against the cv:: shim
+(ORACLE: test infrastructure, not product code; recipe in oracle/Makefile, entry points in oracle/ref_api.cpp).
+
+The library is built in the build container (where /root/reference exists) and travels to the GPU box as a prebuilt file;
+nothing here reads /root/reference at run time."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+from .oracle import KP_DTYPE, _f32, _p, _u8
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+PIN_ALLOC, PIN_SINCOS = 1, 2
+_LIBS = {}
+
+
+def available(variant="libref.so"):
+    return os.path.exists(os.path.join(_HERE, "_ref", variant))
+
+
+def build():
+    """Only possible where the reference tree is present (the build container)."""
+    if os.path.isdir(os.environ.get("REF", "/root/reference")):
+        subprocess.check_call(["make", "-s", "-j8", "-C", _HERE, "ref"])
+
+
+def lib(variant="libref.so"):
+    if variant not in _LIBS:
+        path = os.path.join(_HERE, "_ref", variant)
+        if not os.path.exists(path):
+            build()
+        L = C.CDLL(path)
+        L.ref_orb_create.restype = C.c_void_p
+        L.ref_warp_extract_batch.restype = C.c_long
+        L.ref_cos_fov_th.restype = C.c_float
+        L.ref_arena_used.restype = C.c_size_t
+        _LIBS[variant] = L
+    return _LIBS[variant]
+
+
+class Ref:
+    """One camera configuration of the compiled reference (CamModelGeneral is a process-wide singleton, src/System.cpp:89)."""
+
+    def __init__(self, cam_params, pins=PIN_ALLOC | PIN_SINCOS, variant="libref.so"):
+        self.L = lib(variant)
+        self.cp = cam_params
+        self.L.ref_set_pins(0)
+        self.L.ref_set_camera(C.byref(cam_params))
+        self.pins = pins
+
+    def _pinned(self):
+        self.L.ref_set_camera(C.byref(self.cp))       # singleton: make sure it is this configuration
+        self.L.ref_set_pins(int(self.pins))
+
+    def cos_fov_th(self):
+        return float(self.L.ref_cos_fov_th())
+
+    def build_maps(self):
+        W3, H3 = 3 * self.cp.faceW, 3 * self.cp.faceH
+        m1 = np.empty((H3, W3), np.float32); m2 = np.empty((H3, W3), np.float32)
+        self.L.ref_set_camera(C.byref(self.cp))
+        self.L.ref_build_maps(_p(m1), _p(m2))
+        return m1, m2
+
+    def warp(self, fisheye, m1, m2, canvas=None):
+        fisheye = _u8(fisheye)
+        if canvas is None:
+            canvas = np.zeros((3 * self.cp.faceH, 3 * self.cp.faceW), np.uint8)
+        self.L.ref_set_camera(C.byref(self.cp))
+        self.L.ref_warp(_p(fisheye), _p(m1), _p(m2), _p(canvas))
+        return canvas
+
+    def extractor(self, nfeatures, scaleFactor, nlevels, iniThFAST, minThFAST):
+        return RefORBextractor(self, nfeatures, scaleFactor, nlevels, iniThFAST, minThFAST)
+
+    def warp_extract_batch(self, fisheyes, m1, m2, mask, nfeatures, scaleFactor, nlevels, iniTh, minTh, nthreads):
+        fisheyes = _u8(fisheyes); mask = _u8(mask)
+        self.L.ref_set_camera(C.byref(self.cp))
+        self.L.ref_set_pins(0)                         # the timed baseline runs the stock code paths (glibc malloc / sincosf)
+        return self.L.ref_warp_extract_batch(_p(fisheyes), fisheyes.shape[0], _p(m1), _p(m2), _p(mask), int(nfeatures), C.c_float(scaleFactor), int(nlevels),
+                                             int(iniTh), int(minTh), int(nthreads))
+
+    def descriptor_distance(self, a, b):
+        a = _u8(a); b = _u8(b)
+        return self.L.ref_descriptor_distance(_p(a), _p(b))
+
+
+class RefORBextractor:
+    def __init__(self, ref, nfeatures, scaleFactor, nlevels, iniThFAST, minThFAST):
+        self.ref = ref; self.nlevels = nlevels
+        self._h = C.c_void_p(ref.L.ref_orb_create(int(nfeatures), C.c_float(scaleFactor), int(nlevels), int(iniThFAST), int(minThFAST)))
+
+    def __del__(self):
+        try:
+            self.ref.L.ref_set_pins(0)
+            self.ref.L.ref_orb_destroy(self._h)
+        except Exception:
+            pass
+
+    def __call__(self, image, mask):
+        image = _u8(image); mask = _u8(mask)
+        assert image.shape == mask.shape
+        self.ref._pinned()
+        n = self.ref.L.ref_orb_extract(self._h, _p(image), image.shape[1], image.shape[0], _p(mask))
+        self.ref.L.ref_set_pins(0)
+        kps = np.empty(n, KP_DTYPE); desc = np.empty((n, 32), np.uint8)
+        self.ref.L.ref_orb_result(self._h, _p(kps), _p(desc))
+        return kps, desc
+
+    def level_image(self, level):
+        w = C.c_int(); h = C.c_int()
+        self.ref.L.ref_orb_level_size(self._h, level, C.byref(w), C.byref(h))
+        out = np.zeros((h.value, w.value), np.uint8)
+        self.ref.L.ref_orb_level_image(self._h, level, _p(out))
+        return out

@@ -98,3 +98,11 @@ def test_config4_scale_properties(opt):
     e1 = np.linalg.norm(g["Tcw"][:, :3, 3] - p["Tcw_true"][:, :3, 3], axis=1).mean()
     assert e1 < 0.3 * e0 and 0.03 < g["outlier"].mean() < 0.09
     assert np.allclose(g["Tcw"][0], p["Tcw"][0], atol=1e-6)
+
+
+def test_config4_vs_oracle(oracle, opt):
+    """BASELINE config 4 at full size (50 KF x 20k MapPoints, ~180k cubemap edges, optimize(5)+optimize(10)) against the fp64 oracle:
+    1e-5 relative gate on poses and points, identical LM log (trials / accepted per iteration) and identical outlier set."""
+    p = synth.ba_problem()
+    r, g = _compare_ba(oracle, opt, p)
+    assert len(p["eMP"]) > 150000 and r["iters"] >= 5

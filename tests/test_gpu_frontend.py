@@ -115,3 +115,38 @@ def test_degenerate_frames(oracle, lafida):
     kps, desc = fe.run(flat)
     rk, rd = oracle.ORBextractor(2000, 1.2, 8, 20, 7, 450, 450)(oracle.warp(cp, flat, m1, m2), mask)
     assert np.array_equal(kps.view(np.uint8), rk.view(np.uint8)) and np.array_equal(desc, rd)
+
+
+@pytest.mark.parametrize("face", [560, 570, 610, 333])
+def test_face_size_sweep(oracle, face):
+    """Face sizes whose last FAST cell row / column is shorter than 7 px (ADVICE r1: k_fast indexed shared memory at ny < 0);
+    560 -> level 1, 570 -> level 0, 610 -> level 3 have a 4-row last cell row at scale 1.2."""
+    cfg = config.camera("lafida_cam0_params", CubeFace_w=face, CubeFace_h=face)
+    mask = np.full((3 * face, 3 * face), 255, np.uint8)
+    cp = oracle.cam_params(cfg)
+    m1, m2 = oracle.build_maps(cp)
+    fe = _fe(cfg, mask, max_batch=1)
+    frame = synth.fisheye_frame(cfg, 3)
+    gk, gd = fe.run(frame)
+    rk, rd = oracle.ORBextractor(2000, 1.2, 8, 20, 7, face, face)(oracle.warp(cp, frame, m1, m2), mask)
+    assert len(gk) == len(rk) and len(rk) > 500
+    assert np.array_equal(gk.view(np.uint8), rk.view(np.uint8)) and np.array_equal(gd, rd)
+    fe.close()
+
+
+def test_reference_generated_goldens(lafida):
+    """Golden vectors produced by the reference's own ORBExtractor.cpp / CamModelGeneral.cpp compiled unmodified (oracle/_ref,
+    tests/golden/make_golden_ref.py): config 1 (lafida, 450-px faces) and a config-2 frame (front camera, 650-px faces, 3000 features)."""
+    import os
+    gold = os.path.join(os.path.dirname(__file__), "golden")
+    cfg, mask, cp, maps, fe = lafida
+    g = np.load(os.path.join(gold, "ref_extract_lafida450_frame0.npz"))
+    kps, desc = fe.run(synth.fisheye_frame(cfg, int(g["frame_idx"])))
+    assert np.array_equal(kps.view(np.uint8), g["kps"].view(np.uint8)) and np.array_equal(desc, g["desc"])
+    cfg2 = config.front_1024()
+    fe2 = _fe(cfg2, config.load_mask("gray_cubemap_front_mask_650"), max_batch=1)
+    g = np.load(os.path.join(gold, "ref_extract_front650_frame7.npz"))
+    kps, desc = fe2.run(synth.fisheye_frame(cfg2, int(g["frame_idx"])))
+    assert len(kps) == len(g["kps"]) > 1500
+    assert np.array_equal(kps.view(np.uint8), g["kps"].view(np.uint8)) and np.array_equal(desc, g["desc"])
+    fe2.close()
