@@ -1,64 +1,85 @@
-// Bundle adjustment of libcubemap_b200.so: Optimizer::LocalBundleAdjustment and Optimizer::PoseOptimization on sm_100a.
+// Optimizer::LocalBundleAdjustment of libcubemap_b200.so on sm_100a (PoseOptimization lives in pose_opt.cu).
 //
-// Reference (CPU, g2o): src/Optimizer.cpp:48-451; edges src/g2o_cubemap_vertices_edges.cpp:61-233; LM loop
+// Reference (CPU, g2o): src/Optimizer.cpp:192-451; edge src/g2o_cubemap_vertices_edges.cpp:164-233; LM loop
 // ThirdParty/g2o/g2o/core/optimization_algorithm_levenberg.cpp:61-189; Schur solve core/block_solver.hpp:354-486.
 // The hypergraph is replaced by flat fp64 arrays; all arithmetic stays fp64 (the gate is 1e-5 relative on poses/points),
 // including the reference's float32 round trip inside the projection (ba_math.cuh).
 //
-// Per LM iteration:  k_ba_errors -> k_ba_linearize -> [per trial: k_ba_dinv, k_ba_schur (landmark-sharded across ranks,
-// ncclAllReduce of [S | g | scalars]), k_ba_solve (blocked LDL^T of the <=6P x 6P reduced camera system, one CTA),
-// k_ba_backsub, k_ba_update, k_ba_errors, k_ba_scale].  Control flow (accept/reject, lambda schedule, the ORB-SLAM2
-// stop rule, pbStopFlag) stays on the host like in the reference; one small D2H per trial.
+// Every accumulation is OUTPUT-STATIONARY (no floating-point atomics anywhere), hence bit-reproducible run to run:
+//   k_ba_errors      per edge; chi2 by fixed-shape block sums + a last-block pass over the block partials
+//   k_ba_lin_points  thread per landmark: Hll, bl in registers over the landmark's edges (sorted edge order), Hpl per edge
+//   k_ba_lin_poses   CTA per free pose over its edge list: the 21+6 unique entries of (Hpp, bp)
+//   k_ba_dinv        per landmark (Hll + lambda I)^-1 and Dinv*bl
+//   k_ba_schur       CTA per pose pair (p1 <= p2) over the pair's precomputed co-observation list (edge a1 of p1, edge a2 of p2,
+//                    same landmark, landmark order): S[p1,p2] = [p1==p2] Hpp - sum (B1 Dinv) B2^T, g[p1] = bp - sum B1 (Dinv bl)
+//   k_ba_solve       one thread-block CLUSTER: blocked right-looking LDL^T of the n x n reduced camera system (n = 6 x free poses)
+//                    with the right-hand side carried as an extra row; panel factorisation and trailing update spread over
+//                    the cluster's SMs, panels exchanged through L2, cluster barriers between phases; no size cap
+//   k_ba_backsub / k_ba_update / k_ba_scale / k_ba_restore   landmark back-substitution, oplus (with backup), gain-ratio scale
+// Multi-GPU: landmarks (with their edges) are sharded l % nranks; every rank forms its partial [S | g | bpr | chi2 | scale]
+// and the partials are summed either by one ncclAllReduce or by the one-shot NVLink kernel k_ba_xchg_reduce (peer pointers),
+// in fixed rank order so that every rank solves bit-identical systems.
+// LM control flow (accept/reject, lambda schedule, ORB-SLAM2's stop rule, pbStopFlag) stays on the host like in the reference.
+#include <cooperative_groups.h>
 #include <dlfcn.h>
 #include <algorithm>
 #include <cfloat>
 #include <cstring>
 #include <vector>
-#include "ba_math.cuh"
-#include "common.cuh"
+#include "optimizer.cuh"
+
+namespace cg = cooperative_groups;
 
 namespace cslam {
 
 struct BADev {
-    int nKF, nMP, nE, nP, n;        // nP free active poses, n = 6 nP
+    int nKF, nMP, nE, nQ, nP, n;     // nQ non-fixed key frames (static per call), nP active free poses, n = 6 nP
     double f;                        // fx=fy=cx=cy
     Pose* pose; Pose* poseBak;
     double* X; double* Xbak;
-    const int* eMP; const int* eKF;  // edges sorted by landmark
+    const int* eMP; const int* eKF;  // edges sorted by landmark (stable)
     const double* obs;               // 3 per edge: mx, my, w
     const int8_t* face;
     double* err; uint8_t* level;
-    const int* poseIdx; const uint8_t* ptAct;   // per KF: compact index or -1; per MP: 1 if it has an active edge
+    const int* poseIdx; const uint8_t* ptAct;   // per KF: compact active-free index or -1; per MP: 1 if it has an active edge
+    const int* kfOfQ;                // per candidate pose q: KF index
     const int* lmStart;              // nMP+1, CSR over sorted edges
-    const int* peStart; const int* peList;      // CSR of edge ids by KF
+    const int* peStart; const int* peList;      // CSR of sorted edge ids by KF (ascending = landmark order)
+    const long long* pairStart;      // nQ*nQ+1: co-observation list of (q1,q2), q1<=q2, row-major
+    const int2* tuples;              // (a1, a2)
     double *Hpp, *bp, *Hll, *bl, *Hpl, *Dinv, *db, *xp, *xl;
-    double *S, *g, *bpr;             // one contiguous all-reduce buffer: [S n*n | g n | bpr n] (bpr = full pose gradient for computeScale)
+    double *S, *g, *bpr, *tail;      // one contiguous exchange buffer: [S n*n | g n | bpr n | tail 4]; tail = chi2, scale, -, -
     double* scal;                    // [0] chi2, [1] scale, [2] max diag (as bits), [3] solve flag
+    double* part; unsigned* ticket;  // block partials + arrival counter of the deterministic grid reductions
     int robust; double delta, dsqr;
     int rank, nranks;                // landmark l is owned by rank l % nranks
 };
 
-__device__ __forceinline__ bool owned(const BADev& D, int l) { return (l % D.nranks) == D.rank; }
+__device__ __forceinline__ bool owned(const BADev& D, int l) { return D.nranks == 1 || (l % D.nranks) == D.rank; }
 
-__device__ __forceinline__ double block_sum(double v, double* sh) {
-#pragma unroll
-    for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    if (lane == 0) sh[w] = v;
-    __syncthreads();
-    double r = 0;
-    if (w == 0) {
-        r = lane < (blockDim.x >> 5) ? sh[lane] : 0.0;
-#pragma unroll
-        for (int o = 16; o; o >>= 1) r += __shfl_xor_sync(0xffffffffu, r, o);
+// Deterministic grid-wide sum: fixed-shape block sums, block partials in part[], the last block to arrive adds them in a fixed shape.
+// Returns true in thread 0 of the last block, with the total in *total.
+__device__ __forceinline__ bool grid_sum(double v, double* part, unsigned* ticket, double* sh, double* total) {
+    __shared__ bool last;
+    const double s = block_sum(v, sh);
+    if (threadIdx.x == 0) {
+        part[blockIdx.x] = s;
+        __threadfence();
+        last = atomicAdd(ticket, 1u) == gridDim.x - 1;
     }
     __syncthreads();
-    return r;   // valid in thread 0
+    if (!last) return false;
+    __threadfence();
+    double t = 0;
+    for (unsigned i = threadIdx.x; i < gridDim.x; i += blockDim.x) t += __ldcg(part + i);
+    t = block_sum(t, sh);
+    if (threadIdx.x == 0) { *total = t; *ticket = 0; }
+    return threadIdx.x == 0;
 }
 
-// computeActiveErrors + activeRobustChi2 (partial sum over the landmarks this rank owns)
-__global__ void __launch_bounds__(256) k_ba_errors(BADev D) {
-    __shared__ double sh[8];
+// computeActiveErrors + activeRobustChi2 (partial sum over the landmarks this rank owns) -> *out
+__global__ void __launch_bounds__(256) k_ba_errors(BADev D, double* out) {
+    __shared__ double sh[32];
     const int e = blockIdx.x * blockDim.x + threadIdx.x;
     double c = 0;
     if (e < D.nE && D.level[e] == 0 && owned(D, D.eMP[e])) {
@@ -69,52 +90,111 @@ __global__ void __launch_bounds__(256) k_ba_errors(BADev D) {
         const double chi = D.obs[3 * e + 2] * (er[0] * er[0] + er[1] * er[1]);
         if (D.robust) { double r0, r1; huber(D.delta, D.dsqr, chi, r0, r1); c = r0; } else c = chi;
     }
-    const double s = block_sum(c, sh);
-    if (threadIdx.x == 0 && s != 0.0) atomicAdd(&D.scal[0], s);
+    double tot;
+    if (grid_sum(c, D.part, D.ticket, sh, &tot)) *out = tot;
 }
 
-// buildSystem: linearizeOplus + constructQuadraticForm of every active edge (base_binary_edge.hpp:55-120)
-__global__ void __launch_bounds__(256) k_ba_linearize(BADev D, int useSmem) {
-    extern __shared__ double shH[];   // nP * 42 doubles when useSmem
-    if (useSmem) { for (int i = threadIdx.x; i < D.nP * 42; i += blockDim.x) shH[i] = 0.0; __syncthreads(); }
-    const int e = blockIdx.x * blockDim.x + threadIdx.x;
-    if (e < D.nE && D.level[e] == 0 && owned(D, D.eMP[e])) {
-        const int k = D.eKF[e], l = D.eMP[e], pi = D.poseIdx[k];
-        const Pose T = D.pose[k];
-        double Xc[3], G[2][3], Jp[2][6], Jx[2][3], R[3][3];
-        pose_map(T, D.X + 3 * l, Xc);
-        edge_G(D.face[e], D.f, Xc, G);
-        quat_to_matrix(T.q, R);
-        for (int i = 0; i < 2; i++) for (int j = 0; j < 3; j++) Jx[i][j] = G[i][0] * R[0][j] + G[i][1] * R[1][j] + G[i][2] * R[2][j];
-        const double e0 = D.err[2 * e], e1 = D.err[2 * e + 1], w0 = D.obs[3 * e + 2];
-        double rho1 = 1.0;
-        if (D.robust) { double r0; huber(D.delta, D.dsqr, w0 * (e0 * e0 + e1 * e1), r0, rho1); }
-        const double w = rho1 * w0, r0 = -w * e0, r1 = -w * e1;
+// Jacobians of one active edge (src/g2o_cubemap_vertices_edges.cpp:164-223) and its robust weight / weighted residual
+struct EdgeLin { double Jx[2][3], Jp[2][6], w, r0, r1; };
+__device__ __forceinline__ void linearize_edge(const BADev& D, int e, bool needPose, EdgeLin& L) {
+    const int k = D.eKF[e], l = D.eMP[e];
+    const Pose T = D.pose[k];
+    double Xc[3], G[2][3], R[3][3];
+    pose_map(T, D.X + 3 * l, Xc);
+    edge_G(D.face[e], D.f, Xc, G);
+    quat_to_matrix(T.q, R);
+#pragma unroll
+    for (int i = 0; i < 2; i++)
+#pragma unroll
+        for (int j = 0; j < 3; j++) L.Jx[i][j] = G[i][0] * R[0][j] + G[i][1] * R[1][j] + G[i][2] * R[2][j];
+    if (needPose) edge_Jpose(G, Xc, L.Jp);
+    const double e0 = D.err[2 * e], e1 = D.err[2 * e + 1], w0 = D.obs[3 * e + 2];
+    double rho1 = 1.0;
+    if (D.robust) { double r0; huber(D.delta, D.dsqr, w0 * (e0 * e0 + e1 * e1), r0, rho1); }
+    L.w = rho1 * w0; L.r0 = -L.w * e0; L.r1 = -L.w * e1;
+}
+
+// buildSystem, landmark side (base_binary_edge.hpp:55-120): Hll, bl of one landmark accumulated in registers in edge order, Hpl per edge
+__global__ void __launch_bounds__(128) k_ba_lin_points(BADev D) {
+    const int l = blockIdx.x * blockDim.x + threadIdx.x;
+    if (l >= D.nMP || !owned(D, l)) return;
+    double H[6] = {0, 0, 0, 0, 0, 0}, b[3] = {0, 0, 0};
+    for (int e = D.lmStart[l]; e < D.lmStart[l + 1]; e++) {
+        double* B = D.Hpl + 18 * (size_t)e;
+        const int pi = D.poseIdx[D.eKF[e]];
+        if (D.level[e] != 0) {   // inactive edges contribute zero blocks (the co-observation lists are built once per call)
+#pragma unroll
+            for (int i = 0; i < 18; i++) B[i] = 0.0;
+            continue;
+        }
+        EdgeLin L;
+        linearize_edge(D, e, pi >= 0, L);
+        int q = 0;
+#pragma unroll
         for (int i = 0; i < 3; i++) {
-            atomicAdd(&D.bl[3 * l + i], Jx[0][i] * r0 + Jx[1][i] * r1);
-            for (int j = 0; j < 3; j++) atomicAdd(&D.Hll[9 * l + 3 * i + j], w * (Jx[0][i] * Jx[0][j] + Jx[1][i] * Jx[1][j]));
+            b[i] += L.Jx[0][i] * L.r0 + L.Jx[1][i] * L.r1;
+#pragma unroll
+            for (int j = i; j < 3; j++) H[q++] += L.w * (L.Jx[0][i] * L.Jx[0][j] + L.Jx[1][i] * L.Jx[1][j]);
         }
         if (pi >= 0) {
-            edge_Jpose(G, Xc, Jp);
-            double* Hp = useSmem ? shH + 42 * pi : D.Hpp + 36 * pi;
-            double* bpp = useSmem ? shH + 42 * pi + 36 : D.bp + 6 * pi;
-            for (int i = 0; i < 6; i++) {
-                atomicAdd(&bpp[i], Jp[0][i] * r0 + Jp[1][i] * r1);
-                for (int j = 0; j < 6; j++) atomicAdd(&Hp[6 * i + j], w * (Jp[0][i] * Jp[0][j] + Jp[1][i] * Jp[1][j]));
-                for (int j = 0; j < 3; j++) D.Hpl[18 * (size_t)e + 3 * i + j] = w * (Jp[0][i] * Jx[0][j] + Jp[1][i] * Jx[1][j]);
-            }
+#pragma unroll
+            for (int i = 0; i < 6; i++)
+#pragma unroll
+                for (int j = 0; j < 3; j++) B[3 * i + j] = L.w * (L.Jp[0][i] * L.Jx[0][j] + L.Jp[1][i] * L.Jx[1][j]);
+        } else {
+#pragma unroll
+            for (int i = 0; i < 18; i++) B[i] = 0.0;
         }
     }
-    if (useSmem) {
-        __syncthreads();
-        for (int i = threadIdx.x; i < D.nP * 42; i += blockDim.x) {
-            const double v = shH[i];
-            if (v != 0.0) { const int p = i / 42, r = i - 42 * p; atomicAdd(r < 36 ? &D.Hpp[36 * p + r] : &D.bp[6 * p + r - 36], v); }
-        }
-    }
+    double* Hl = D.Hll + 9 * (size_t)l;
+    Hl[0] = H[0]; Hl[1] = H[1]; Hl[2] = H[2]; Hl[3] = H[1]; Hl[4] = H[3]; Hl[5] = H[4]; Hl[6] = H[2]; Hl[7] = H[4]; Hl[8] = H[5];
+    D.bl[3 * l] = b[0]; D.bl[3 * l + 1] = b[1]; D.bl[3 * l + 2] = b[2];
 }
 
-// computeLambdaInit: max |H_jj| over all active free vertices
+// buildSystem, pose side: CTA per candidate pose over its edge list; 21 unique entries of Hpp + 6 of bp
+__global__ void __launch_bounds__(256) k_ba_lin_poses(BADev D) {
+    __shared__ double red[8][28];
+    const int k = D.kfOfQ[blockIdx.x], p = D.poseIdx[k];
+    if (p < 0) return;
+    double acc[27];
+#pragma unroll
+    for (int i = 0; i < 27; i++) acc[i] = 0.0;
+    for (int q = D.peStart[k] + threadIdx.x; q < D.peStart[k + 1]; q += blockDim.x) {
+        const int e = D.peList[q];
+        if (D.level[e] != 0 || !owned(D, D.eMP[e])) continue;
+        EdgeLin L;
+        linearize_edge(D, e, true, L);
+        int t = 0;
+#pragma unroll
+        for (int a = 0; a < 6; a++)
+#pragma unroll
+            for (int b = a; b < 6; b++) acc[t++] += L.w * (L.Jp[0][a] * L.Jp[0][b] + L.Jp[1][a] * L.Jp[1][b]);
+#pragma unroll
+        for (int a = 0; a < 6; a++) acc[21 + a] += L.Jp[0][a] * L.r0 + L.Jp[1][a] * L.r1;
+    }
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+#pragma unroll
+    for (int i = 0; i < 27; i++) {
+        double v = acc[i];
+#pragma unroll
+        for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if (lane == 0) red[w][i] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x < 27) {
+        double s = 0;
+        for (int ww = 0; ww < 8; ww++) s += red[ww][threadIdx.x];
+        red[0][threadIdx.x] = s;
+    }
+    __syncthreads();
+    if (threadIdx.x < 36) {
+        const int a = threadIdx.x / 6, b = threadIdx.x % 6, lo = min(a, b), hi = max(a, b);
+        D.Hpp[36 * p + threadIdx.x] = red[0][lo * 6 - lo * (lo - 1) / 2 + (hi - lo)];
+    }
+    if (threadIdx.x < 6) D.bp[6 * p + threadIdx.x] = red[0][21 + threadIdx.x];
+}
+
+// computeLambdaInit: max |H_jj| over all active free vertices (integer atomicMax of the bit pattern: order independent)
 __global__ void __launch_bounds__(256) k_ba_maxdiag(BADev D) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     double m = 0;
@@ -129,9 +209,17 @@ __global__ void __launch_bounds__(256) k_ba_maxdiag(BADev D) {
 // Dinv = (Hll + lambda I)^-1 (3x3 cofactors, like Eigen), db = Dinv * bl
 __global__ void __launch_bounds__(256) k_ba_dinv(BADev D, double lambda) {
     const int l = blockIdx.x * blockDim.x + threadIdx.x;
-    if (l >= D.nMP || !D.ptAct[l] || !owned(D, l)) return;
+    if (l >= D.nMP || !owned(D, l)) return;
+    double* Dv = D.Dinv + 9 * (size_t)l;
+    if (!D.ptAct[l]) {
+#pragma unroll
+        for (int i = 0; i < 9; i++) Dv[i] = 0.0;
+        D.db[3 * l] = 0; D.db[3 * l + 1] = 0; D.db[3 * l + 2] = 0;
+        return;
+    }
     double M[9];
-    for (int i = 0; i < 9; i++) M[i] = D.Hll[9 * l + i];
+#pragma unroll
+    for (int i = 0; i < 9; i++) M[i] = D.Hll[9 * (size_t)l + i];
     M[0] += lambda; M[4] += lambda; M[8] += lambda;
     const double c00 = M[4] * M[8] - M[5] * M[7], c01 = M[5] * M[6] - M[3] * M[8], c02 = M[3] * M[7] - M[4] * M[6];
     const double id = 1.0 / (M[0] * c00 + M[1] * c01 + M[2] * c02);
@@ -139,181 +227,297 @@ __global__ void __launch_bounds__(256) k_ba_dinv(BADev D, double lambda) {
     Di[0] = c00 * id; Di[1] = (M[2] * M[7] - M[1] * M[8]) * id; Di[2] = (M[1] * M[5] - M[2] * M[4]) * id;
     Di[3] = c01 * id; Di[4] = (M[0] * M[8] - M[2] * M[6]) * id; Di[5] = (M[2] * M[3] - M[0] * M[5]) * id;
     Di[6] = c02 * id; Di[7] = (M[1] * M[6] - M[0] * M[7]) * id; Di[8] = (M[0] * M[4] - M[1] * M[3]) * id;
-    for (int i = 0; i < 9; i++) D.Dinv[9 * l + i] = Di[i];
+#pragma unroll
+    for (int i = 0; i < 9; i++) Dv[i] = Di[i];
+#pragma unroll
     for (int i = 0; i < 3; i++) D.db[3 * l + i] = Di[3 * i] * D.bl[3 * l] + Di[3 * i + 1] * D.bl[3 * l + 1] + Di[3 * i + 2] * D.bl[3 * l + 2];
 }
 
-// S = Hpp(partial) ; g = bp(partial)   (lambda is added to the diagonal after the all-reduce)
-__global__ void __launch_bounds__(256) k_ba_s_init(BADev D) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < D.n * D.n) {
-        const int r = i / D.n, c = i - r * D.n;
-        D.S[i] = (r / 6 == c / 6) ? D.Hpp[36 * (r / 6) + 6 * (r % 6) + (c % 6)] : 0.0;
-    }
-    if (i < D.n) { D.g[i] = D.bp[i]; D.bpr[i] = D.bp[i]; }
+// ---- co-observation lists: for every pair of candidate poses q1 <= q2 the (a1, a2) edge pairs that share a landmark, in landmark order.
+// Built once per cslam_local_ba call over ALL edges (edges that become inactive later carry zero Hpl blocks).
+__device__ __forceinline__ int partner_edge(const BADev& D, int a1, int k2) {
+    const int l = D.eMP[a1];
+    for (int a2 = D.lmStart[l]; a2 < D.lmStart[l + 1]; a2++) if (D.eKF[a2] == k2) return a2;
+    return -1;
 }
-__global__ void __launch_bounds__(256) k_ba_add_lambda(BADev D, double lambda) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < D.n) D.S[(size_t)i * D.n + i] += lambda;
+__global__ void __launch_bounds__(128) k_ba_pairs_count(BADev D, long long* cnt) {
+    __shared__ int wsum[4];
+    const int q1 = blockIdx.y, q2 = blockIdx.x;
+    if (q1 > q2) { if (threadIdx.x == 0) cnt[(size_t)q1 * D.nQ + q2] = 0; return; }
+    const int k1 = D.kfOfQ[q1], k2 = D.kfOfQ[q2], beg = D.peStart[k1], end = D.peStart[k1 + 1];
+    if (q1 == q2) { if (threadIdx.x == 0) cnt[(size_t)q1 * D.nQ + q2] = end - beg; return; }
+    int c = 0;
+    for (int q = beg + threadIdx.x; q < end; q += blockDim.x) c += partner_edge(D, D.peList[q], k2) >= 0;
+#pragma unroll
+    for (int o = 16; o; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+    if ((threadIdx.x & 31) == 0) wsum[threadIdx.x >> 5] = c;
+    __syncthreads();
+    if (threadIdx.x == 0) cnt[(size_t)q1 * D.nQ + q2] = wsum[0] + wsum[1] + wsum[2] + wsum[3];
+}
+// exclusive scan of `m` counts (in place) + total, one CTA
+__global__ void __launch_bounds__(1024) k_ba_pairs_scan(long long* v, int m) {
+    __shared__ long long wtot[32];
+    __shared__ long long carry;
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    for (int base = 0; base < m; base += 1024) {
+        const int i = base + threadIdx.x;
+        const long long x = i < m ? v[i] : 0;
+        long long s = x;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const long long t = __shfl_up_sync(0xffffffffu, s, o); if (lane >= o) s += t; }
+        if (lane == 31) wtot[w] = s;
+        __syncthreads();
+        if (w == 0) {
+            long long t = wtot[lane];
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const long long u = __shfl_up_sync(0xffffffffu, t, o); if (lane >= o) t += u; }
+            wtot[lane] = t;
+        }
+        __syncthreads();
+        const long long excl = carry + (w ? wtot[w - 1] : 0) + s - x;
+        if (i < m) v[i] = excl;
+        __syncthreads();
+        if (threadIdx.x == 1023) carry = excl + x;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) v[m] = carry;
+}
+__global__ void __launch_bounds__(128) k_ba_pairs_fill(BADev D, const long long* start, int2* tuples) {
+    __shared__ int wcnt[4];
+    __shared__ long long base;
+    const int q1 = blockIdx.y, q2 = blockIdx.x;
+    if (q1 > q2) return;
+    const int k1 = D.kfOfQ[q1], k2 = D.kfOfQ[q2], beg = D.peStart[k1], end = D.peStart[k1 + 1];
+    int2* out = tuples + start[(size_t)q1 * D.nQ + q2];
+    if (q1 == q2) { for (int q = beg + threadIdx.x; q < end; q += blockDim.x) { const int a = D.peList[q]; out[q - beg] = make_int2(a, a); } return; }
+    if (threadIdx.x == 0) base = 0;
+    __syncthreads();
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    for (int q0 = beg; q0 < end; q0 += blockDim.x) {   // ordered compaction: output order = order of the pose's edge list = landmark order
+        const int q = q0 + threadIdx.x;
+        int a1 = -1, a2 = -1;
+        if (q < end) { a1 = D.peList[q]; a2 = partner_edge(D, a1, k2); }
+        const unsigned ball = __ballot_sync(0xffffffffu, a2 >= 0);
+        if (lane == 0) wcnt[w] = __popc(ball);
+        __syncthreads();
+        int pre = 0;
+        for (int ww = 0; ww < w; ww++) pre += wcnt[ww];
+        if (a2 >= 0) out[base + pre + __popc(ball & ((1u << lane) - 1))] = make_int2(a1, a2);
+        __syncthreads();
+        if (threadIdx.x == 0) base += wcnt[0] + wcnt[1] + wcnt[2] + wcnt[3];
+        __syncthreads();
+    }
 }
 
-// Schur complement, reference block_solver.hpp:381-439: for every landmark and every ordered pair of its observations
-// (a1,a2): S[p1,p2] -= (B1 Dinv) B2^T, g[p1] -= B1 (Dinv bl). One CTA = a chunk of the edges of one pose p1 (row block of S
-// accumulated in shared memory), one warp = one edge a1 at a time.
-__global__ void __launch_bounds__(256) k_ba_schur(BADev D, int chunks) {
-    extern __shared__ double shS[];   // 6 x n row block + 6 (g)
-    const int k1 = blockIdx.y, p1 = D.poseIdx[k1];
-    if (p1 < 0) return;
-    const int n = D.n;
-    for (int i = threadIdx.x; i < 6 * n + 6; i += blockDim.x) shS[i] = 0.0;
-    __syncthreads();
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
-    const int beg = D.peStart[k1], end = D.peStart[k1 + 1];
-    for (int q = beg + blockIdx.x * nw + warp; q < end; q += chunks * nw) {
-        const int a1 = D.peList[q];
-        if (D.level[a1] != 0) continue;
-        const int l = D.eMP[a1];
+// Schur complement (block_solver.hpp:381-439), output-stationary: one CTA per pose pair accumulates its 6x6 block in registers over the
+// pair's co-observation list, then a fixed-shape reduction. The diagonal pair also forms g = bp - sum B (Dinv bl) and bpr = bp.
+static const int SCHUR_T = 128;
+__global__ void __launch_bounds__(SCHUR_T) k_ba_schur(BADev D, double lambdaDiag) {
+    __shared__ double red[SCHUR_T / 32][44];
+    const int q1 = blockIdx.y, q2 = blockIdx.x;
+    if (q1 > q2) return;
+    const int p1 = D.poseIdx[D.kfOfQ[q1]], p2 = D.poseIdx[D.kfOfQ[q2]];
+    if (p1 < 0 || p2 < 0) return;
+    const bool diag = q1 == q2;
+    double acc[42];
+#pragma unroll
+    for (int i = 0; i < 42; i++) acc[i] = 0.0;
+    const long long beg = D.pairStart[(size_t)q1 * D.nQ + q2], end = D.pairStart[(size_t)q1 * D.nQ + q2 + 1];
+    for (long long t = beg + threadIdx.x; t < end; t += SCHUR_T) {
+        const int2 tp = D.tuples[t];
+        const int l = D.eMP[tp.x];
         if (!owned(D, l)) continue;
-        const double* B1 = D.Hpl + 18 * (size_t)a1;
-        const double* Di = D.Dinv + 9 * l;
-        // BD (6x3): lanes 0..17
-        double bd = 0;
-        if (lane < 18) { const int i = lane / 3, j = lane % 3; bd = B1[3 * i] * Di[j] + B1[3 * i + 1] * Di[3 + j] + B1[3 * i + 2] * Di[6 + j]; }
-        if (lane < 6) atomicAdd(&shS[6 * n + lane], -(B1[3 * lane] * D.db[3 * l] + B1[3 * lane + 1] * D.db[3 * l + 1] + B1[3 * lane + 2] * D.db[3 * l + 2]));
-        const int s = D.lmStart[l], t = D.lmStart[l + 1];
-        // 36 outputs per partner: lane handles elements lane and lane+32 (<36)
-        for (int a2 = s; a2 < t; a2++) {
-            if (D.level[a2] != 0) continue;
-            const int p2 = D.poseIdx[D.eKF[a2]];
-            if (p2 < 0) continue;
-            const double* B2 = D.Hpl + 18 * (size_t)a2;
+        const double* B1 = D.Hpl + 18 * (size_t)tp.x;
+        const double* B2 = D.Hpl + 18 * (size_t)tp.y;
+        const double* Di = D.Dinv + 9 * (size_t)l;
+        double b1[18], di[9], b2[18];
 #pragma unroll
-            for (int rep = 0; rep < 2; rep++) {
-                const int el = lane + 32 * rep;
-                const int i = el / 6, j = el - 6 * i;   // rows of B1 x rows of B2
-                double v = 0;
+        for (int i = 0; i < 18; i++) { b1[i] = B1[i]; b2[i] = B2[i]; }
 #pragma unroll
-                for (int c = 0; c < 3; c++) v += __shfl_sync(0xffffffffu, bd, (el < 36 ? i : 0) * 3 + c) * (el < 36 ? B2[3 * j + c] : 0.0);
-                if (el < 36) atomicAdd(&shS[i * n + 6 * p2 + j], -v);
-            }
+        for (int i = 0; i < 9; i++) di[i] = Di[i];
+#pragma unroll
+        for (int i = 0; i < 6; i++) {
+            const double t0 = b1[3 * i] * di[0] + b1[3 * i + 1] * di[3] + b1[3 * i + 2] * di[6];
+            const double t1 = b1[3 * i] * di[1] + b1[3 * i + 1] * di[4] + b1[3 * i + 2] * di[7];
+            const double t2 = b1[3 * i] * di[2] + b1[3 * i + 1] * di[5] + b1[3 * i + 2] * di[8];
+#pragma unroll
+            for (int j = 0; j < 6; j++) acc[6 * i + j] += t0 * b2[3 * j] + t1 * b2[3 * j + 1] + t2 * b2[3 * j + 2];
+        }
+        if (diag) {
+            const double d0 = D.db[3 * l], d1 = D.db[3 * l + 1], d2 = D.db[3 * l + 2];
+#pragma unroll
+            for (int i = 0; i < 6; i++) acc[36 + i] += b1[3 * i] * d0 + b1[3 * i + 1] * d1 + b1[3 * i + 2] * d2;
         }
     }
-    __syncthreads();
-    for (int i = threadIdx.x; i < 6 * n; i += blockDim.x) {
-        const double v = shS[i];
-        if (v != 0.0) atomicAdd(&D.S[(size_t)(6 * p1 + i / n) * n + (i % n)], v);
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+#pragma unroll
+    for (int i = 0; i < 42; i++) {
+        if (i >= 36 && !diag) break;
+        double v = acc[i];
+#pragma unroll
+        for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if (lane == 0) red[w][i] = v;
     }
-    if (threadIdx.x < 6) { const double v = shS[6 * n + threadIdx.x]; if (v != 0.0) atomicAdd(&D.g[6 * p1 + threadIdx.x], v); }
+    __syncthreads();
+    const int n = D.n;
+    if (threadIdx.x < 36) {
+        const int i = threadIdx.x / 6, j = threadIdx.x % 6;
+        double s = 0;
+#pragma unroll
+        for (int ww = 0; ww < SCHUR_T / 32; ww++) s += red[ww][threadIdx.x];
+        double v = -s;
+        if (diag) { v += D.Hpp[36 * p1 + threadIdx.x]; if (i == j) v += lambdaDiag; }
+        D.S[(size_t)(6 * p1 + i) * n + 6 * p2 + j] = v;
+        if (!diag) D.S[(size_t)(6 * p2 + j) * n + 6 * p1 + i] = v;
+    } else if (diag && threadIdx.x < 42) {
+        const int i = threadIdx.x - 36;
+        double s = 0;
+#pragma unroll
+        for (int ww = 0; ww < SCHUR_T / 32; ww++) s += red[ww][threadIdx.x];
+        const double b = D.bp[6 * p1 + i];
+        D.g[6 * p1 + i] = b - s;
+        D.bpr[6 * p1 + i] = b;
+    }
 }
 
-// Dense LDL^T (no pivoting) + solve of the n x n reduced camera system in one CTA, blocked (panel NB) so that the O(n^3)
-// work reads the panel from shared memory. scal[3] = 1 on a zero / non-finite pivot (LinearSolverEigen's failure).
+// ---------------------------------------------------------------------------------------------- reduced camera system solve
+// Blocked right-looking LDL^T (no pivoting; LinearSolverEigen's SimplicialLDLT has none either) of the n x n system in ONE thread-block
+// cluster. The right-hand side g sits right behind S, i.e. it is row n of an (n+1) x n matrix: carrying it through the factorisation
+// as one more row performs the forward substitution (row n of L = D^-1 L^-1 g). Per panel of NB columns:
+//   (1) every CTA factors the NB x NB diagonal block redundantly (shared memory, all 256 threads, two barriers per column);
+//   (2) the rows below are NB-step forward substitutions, one thread per row, rows dealt round-robin to the CTAs of the cluster;
+//       L goes back into S (row-major, for the back substitution) and L, L*d go to the transposed panel buffers Lt / LDt;
+//   (3) cluster barrier; trailing update with 4x2 register tiles, tiles dealt over all threads of the cluster, panel values
+//       streamed from L2 (coalesced, L1 bypassed); cluster barrier.
+// scal[3] = 1 on a zero / non-finite pivot (LinearSolverEigen's failure): the LM trial is rejected.
 static const int LD_NB = 32;
-// Blocked right-looking LDL^T in one CTA. The right-hand side g is stored right behind S, i.e. it is row n of an (n+1) x n
-// matrix: carrying it through the factorisation as one more row performs the forward substitution for free (row n of L =
-// D^-1 L^-1 g). Per panel of NB columns: (1) warp 0 factors the NB x NB diagonal block with warp-level sync only,
-// (2) every row below is a NB-step forward substitution against it, one thread per row, no block syncs,
-// (3) trailing update with 4x2 register tiles from the shared-memory panel. Back substitution is blocked the same way.
-__global__ void __launch_bounds__(1024) k_ba_solve(BADev D) {
-    extern __shared__ double sm[];   // panel L: (n+1) x (NB+1) ; panel L*d: same ; d: n ; x: n
-    const int n = D.n, T = blockDim.x, tid = threadIdx.x, PS = LD_NB + 1, lane = tid & 31, warp = tid >> 5;
-    double* A = D.S;                 // (n+1) x n, lower triangle + row n used; overwritten by L (unit diagonal implied)
-    double* P = sm; double* PD = P + (size_t)(n + 1) * PS; double* dvec = PD + (size_t)(n + 1) * PS; double* y = dvec + n;
+static const int SOLVE_T = 256;
+
+__global__ void __launch_bounds__(SOLVE_T) k_ba_solve(BADev D, double* __restrict__ Lt, double* __restrict__ LDt, int ldp) {
+    extern __shared__ double ysm[];                 // back substitution: y[n]
+    __shared__ double Pd[LD_NB][LD_NB + 1];         // diagonal block: L below the diagonal after (1)
+    __shared__ double PDd[LD_NB][LD_NB + 1];        // L * d
+    __shared__ double dvec[LD_NB];
     __shared__ int fail;
+    cg::cluster_group cluster = cg::this_cluster();
+    const int C = cluster.num_blocks(), crank = cluster.block_rank();
+    const int n = D.n, tid = threadIdx.x;
+    double* A = D.S;
     if (tid == 0) fail = 0;
     __syncthreads();
     for (int jb = 0; jb < n; jb += LD_NB) {
         const int nb = min(LD_NB, n - jb), rows = n + 1 - jb;
-        for (int i = tid; i < rows * nb; i += T) { const int r = i / nb, c = i - r * nb; P[r * PS + c] = A[(size_t)(jb + r) * n + jb + c]; }
+        // (1) diagonal block
+        for (int i = tid; i < LD_NB * LD_NB; i += SOLVE_T) {
+            const int r = i / LD_NB, c = i - r * LD_NB;
+            Pd[r][c] = (r < nb && c < nb && c <= r) ? __ldcg(A + (size_t)(jb + r) * n + jb + c) : 0.0;
+        }
         __syncthreads();
-        // (1) diagonal block: lane = row
-        if (warp == 0) {
+        {
+            const int r = tid >> 3, cg4 = (tid & 7) * 4;   // thread owns elements (r, cg4 .. cg4+3)
             for (int c = 0; c < nb; c++) {
-                const double dc = P[c * PS + c];
-                if (lane == 0) { if (dc == 0.0 || !isfinite(dc)) fail = 1; dvec[jb + c] = dc; }
-                if (lane > c && lane < nb) {
-                    const double v = P[lane * PS + c];
-                    PD[lane * PS + c] = v; P[lane * PS + c] = v / dc;
+                const double dc = Pd[c][c];
+                if (tid == 0) { if (dc == 0.0 || !isfinite(dc)) fail = 1; dvec[c] = dc; }
+                if ((c >> 2) == (tid & 7) && r > c && r < nb) { const double v = Pd[r][c]; PDd[r][c] = v; Pd[r][c] = v / dc; }
+                __syncthreads();
+                if (r > c && r < nb) {
+                    const double ld = PDd[r][c];
+#pragma unroll
+                    for (int k = 0; k < 4; k++) { const int c2 = cg4 + k; if (c2 > c && c2 <= r) Pd[r][c2] -= ld * Pd[c2][c]; }
                 }
-                __syncwarp();
-                if (lane > c && lane < nb)
-                    for (int c2 = c + 1; c2 <= lane; c2++) P[lane * PS + c2] -= PD[lane * PS + c] * P[c2 * PS + c];
-                __syncwarp();
+                __syncthreads();
             }
         }
-        __syncthreads();
-        if (fail) break;
-        // (2) rows below the diagonal block (including the rhs row): v_c = a_c - sum_{c'<c} (L d)[r][c'] L[c][c'] ; L[r][c] = v_c / d_c
-        for (int r = nb + tid; r < rows; r += T) {
-            double* Pr = P + (size_t)r * PS; double* PDr = PD + (size_t)r * PS;
-            for (int c = 0; c < nb; c++) {
-                double v = Pr[c];
-                const double* Lc = P + (size_t)c * PS;
-                for (int c2 = 0; c2 < c; c2++) v -= PDr[c2] * Lc[c2];
-                PDr[c] = v; Pr[c] = v / dvec[jb + c];
+        if (fail) break;   // block-uniform and identical in every CTA of the cluster (same data)
+        // (2) rows below the diagonal block (including the rhs row)
+        const int trR = rows - nb;
+        for (int rr = crank * SOLVE_T + tid; rr < trR; rr += C * SOLVE_T) {
+            double* Arow = A + (size_t)(jb + nb + rr) * n + jb;
+            double x[LD_NB];
+#pragma unroll
+            for (int c = 0; c < LD_NB; c++) x[c] = c < nb ? __ldcg(Arow + c) : 0.0;
+#pragma unroll
+            for (int c = 0; c < LD_NB; c++) {
+                if (c < nb) {
+                    double v = x[c];
+#pragma unroll
+                    for (int c2 = 0; c2 < c; c2++) v -= x[c2] * Pd[c][c2];
+                    x[c] = v;
+                    const double lv = v / dvec[c];
+                    Arow[c] = lv;
+                    Lt[(size_t)c * ldp + rr] = lv; LDt[(size_t)c * ldp + rr] = v;
+                }
             }
         }
-        __syncthreads();
-        // write L panel back, then trailing update A[i][k] -= sum_c (L[i][c] d_c) L[k][c] for rows i >= cols k >= jb+nb, 4x2 tiles
-        for (int i = tid; i < rows * nb; i += T) { const int r = i / nb, c = i - r * nb; if (r > c) A[(size_t)(jb + r) * n + jb + c] = P[r * PS + c]; }
-        const int trR = rows - nb, trC = n - jb - nb;      // rows include the rhs row, columns do not
-        const int tR = (trR + 3) >> 2, tC = (trC + 1) >> 1;
-        for (int i = tid; i < tR * tC; i += T) {
-            const int br = i / tC, bc = i - br * tC;
-            const int r0 = 4 * br, k0 = 2 * bc;
-            if (k0 > r0 + 3) continue;                      // tile entirely above the diagonal
-            const double* Lr[4]; const double* Lk[2];
+        // L of the diagonal block back into S (needed by the back substitution), by cluster rank 0
+        if (crank == 0)
+            for (int i = tid; i < nb * nb; i += SOLVE_T) { const int r = i / nb, c = i - r * nb; if (r > c) A[(size_t)(jb + r) * n + jb + c] = Pd[r][c]; }
+        cluster.sync();
+        // (3) trailing update A[i][k] -= sum_c (L d)[i][c] L[k][c], rows i include the rhs row, columns k < trC, k <= i
+        const int trC = n - jb - nb;
+        if (trC > 0) {
+            const int tR = (trR + 3) >> 2, tC = (trC + 1) >> 1;
+            for (int i = crank * SOLVE_T + tid; i < tR * tC; i += C * SOLVE_T) {
+                const int br = i / tC, bc = i - br * tC;
+                const int r0 = 4 * br, k0 = 2 * bc;
+                if (k0 > r0 + 3) continue;   // tile entirely above the diagonal
+                double acc[4][2] = {{0, 0}, {0, 0}, {0, 0}, {0, 0}};
+#pragma unroll 8
+                for (int c = 0; c < nb; c++) {
+                    const double2 bv = __ldcg(reinterpret_cast<const double2*>(Lt + (size_t)c * ldp + k0));
+                    const double2 a01 = __ldcg(reinterpret_cast<const double2*>(LDt + (size_t)c * ldp + r0));
+                    const double2 a23 = __ldcg(reinterpret_cast<const double2*>(LDt + (size_t)c * ldp + r0 + 2));
+                    acc[0][0] += a01.x * bv.x; acc[0][1] += a01.x * bv.y;
+                    acc[1][0] += a01.y * bv.x; acc[1][1] += a01.y * bv.y;
+                    acc[2][0] += a23.x * bv.x; acc[2][1] += a23.x * bv.y;
+                    acc[3][0] += a23.y * bv.x; acc[3][1] += a23.y * bv.y;
+                }
 #pragma unroll
-            for (int a = 0; a < 4; a++) Lr[a] = PD + (size_t)(nb + min(r0 + a, trR - 1)) * PS;
-#pragma unroll
-            for (int bq = 0; bq < 2; bq++) Lk[bq] = P + (size_t)(nb + min(k0 + bq, trC - 1)) * PS;
-            double acc[4][2] = {{0, 0}, {0, 0}, {0, 0}, {0, 0}};
-            for (int c = 0; c < nb; c++) {
-                const double b0 = Lk[0][c], b1 = Lk[1][c];
-#pragma unroll
-                for (int a = 0; a < 4; a++) { const double av = Lr[a][c]; acc[a][0] += av * b0; acc[a][1] += av * b1; }
-            }
-#pragma unroll
-            for (int a = 0; a < 4; a++) {
-                const int r = r0 + a;
-                if (r >= trR) break;
-                double* dst = A + (size_t)(jb + nb + r) * n + jb + nb;
-                if (k0 <= r && k0 < trC) dst[k0] -= acc[a][0];
-                if (k0 + 1 <= r && k0 + 1 < trC) dst[k0 + 1] -= acc[a][1];
+                for (int a = 0; a < 4; a++) {
+                    const int r = r0 + a;
+                    if (r >= trR) break;
+                    double* dst = A + (size_t)(jb + nb + r) * n + jb + nb;
+                    if (k0 <= r && k0 < trC) dst[k0] -= acc[a][0];
+                    if (k0 + 1 <= r && k0 + 1 < trC) dst[k0 + 1] -= acc[a][1];
+                }
             }
         }
-        __syncthreads();
+        cluster.sync();
     }
-    if (fail) { if (tid == 0) D.scal[3] = 1.0; return; }
-    // backward: L^T x = z, z = row n of L (= D^-1 L^-1 g); processed in blocks of NB columns from the bottom
-    for (int i = tid; i < n; i += T) y[i] = A[(size_t)n * n + i];
+    if (fail) { if (crank == 0 && tid == 0) D.scal[3] = 1.0; return; }
+    if (crank != 0) return;
+    // backward: L^T x = z, z = row n of L (= D^-1 L^-1 g); blocks of NB columns from the bottom
+    double* y = ysm;
+    for (int i = tid; i < n; i += SOLVE_T) y[i] = __ldcg(A + (size_t)n * n + i);
     __syncthreads();
     for (int je = n; je > 0; je -= LD_NB) {
         const int j0 = max(je - LD_NB, 0), nb = je - j0;
-        // load the nb x nb diagonal block of L into P (row-major), solve it with warp 0: x_j final for j in [j0, je)
-        for (int i = tid; i < nb * nb; i += T) { const int r = i / nb, c = i - r * nb; P[r * PS + c] = (r > c) ? A[(size_t)(j0 + r) * n + j0 + c] : 0.0; }
+        for (int i = tid; i < nb * nb; i += SOLVE_T) { const int r = i / nb, c = i - r * nb; Pd[r][c] = (r > c) ? __ldcg(A + (size_t)(j0 + r) * n + j0 + c) : 0.0; }
         __syncthreads();
-        if (warp == 0) {
+        if (tid < 32) {
             for (int j = nb - 1; j >= 0; j--) {
                 const double xj = y[j0 + j];
-                if (lane < j) y[j0 + lane] -= P[j * PS + lane] * xj;
+                if (tid < j) y[j0 + tid] -= Pd[j][tid] * xj;
                 __syncwarp();
             }
         }
         __syncthreads();
         // rows above: y[i] -= sum_{j in block} L[j][i] x_j   (rows of L are contiguous: coalesced over i)
-        for (int i = tid; i < j0; i += T) {
+        for (int i = tid; i < j0; i += SOLVE_T) {
             double s = 0;
-            for (int j = 0; j < nb; j++) s += A[(size_t)(j0 + j) * n + i] * y[j0 + j];
+#pragma unroll 8
+            for (int j = 0; j < nb; j++) s += __ldcg(A + (size_t)(j0 + j) * n + i) * y[j0 + j];
             y[i] -= s;
         }
         __syncthreads();
     }
-    for (int i = tid; i < n; i += T) D.xp[i] = y[i];
+    for (int i = tid; i < n; i += SOLVE_T) D.xp[i] = y[i];
 }
 
 // xl = Dinv (bl - Hpl^T xp)   (block_solver.hpp:461-481)
-__global__ void __launch_bounds__(256) k_ba_backsub(BADev D) {
+__global__ void __launch_bounds__(128) k_ba_backsub(BADev D) {
     const int l = blockIdx.x * blockDim.x + threadIdx.x;
     if (l >= D.nMP) return;
     if (!D.ptAct[l] || !owned(D, l)) { D.xl[3 * l] = 0; D.xl[3 * l + 1] = 0; D.xl[3 * l + 2] = 0; return; }
@@ -323,30 +527,47 @@ __global__ void __launch_bounds__(256) k_ba_backsub(BADev D) {
         const int p = D.poseIdx[D.eKF[a]];
         if (p < 0) continue;
         const double* B = D.Hpl + 18 * (size_t)a;
-        for (int j = 0; j < 3; j++) { double s = 0; for (int i = 0; i < 6; i++) s += B[3 * i + j] * D.xp[6 * p + i]; cl[j] -= s; }
+        const double* xq = D.xp + 6 * p;
+#pragma unroll
+        for (int j = 0; j < 3; j++) { double s = 0;
+#pragma unroll
+            for (int i = 0; i < 6; i++) s += B[3 * i + j] * xq[i]; cl[j] -= s; }
     }
-    const double* Di = D.Dinv + 9 * l;
+    const double* Di = D.Dinv + 9 * (size_t)l;
+#pragma unroll
     for (int i = 0; i < 3; i++) D.xl[3 * l + i] = Di[3 * i] * cl[0] + Di[3 * i + 1] * cl[1] + Di[3 * i + 2] * cl[2];
 }
 
+__device__ __noinline__ Pose pose_oplus_ba(const Pose& est, const double* u) { return pose_oplus(est, u); }
+
+// push() + oplus (base_vertex.h:96-99, types_six_dof_expmap.h:73-76, types_sba.h:52-56)
 __global__ void __launch_bounds__(256) k_ba_update(BADev D) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < D.nKF) { const int p = D.poseIdx[i]; if (p >= 0) D.pose[i] = pose_oplus(D.pose[i], D.xp + 6 * p); }
-    if (i < D.nMP && D.ptAct[i] && owned(D, i)) { D.X[3 * i] += D.xl[3 * i]; D.X[3 * i + 1] += D.xl[3 * i + 1]; D.X[3 * i + 2] += D.xl[3 * i + 2]; }
+    if (i < D.nKF) { const Pose T = D.pose[i]; D.poseBak[i] = T; const int p = D.poseIdx[i]; if (p >= 0) D.pose[i] = pose_oplus_ba(T, D.xp + 6 * p); }
+    if (i < D.nMP) {
+        const double x = D.X[3 * i], y = D.X[3 * i + 1], z = D.X[3 * i + 2];
+        D.Xbak[3 * i] = x; D.Xbak[3 * i + 1] = y; D.Xbak[3 * i + 2] = z;
+        if (D.ptAct[i] && owned(D, i)) { D.X[3 * i] = x + D.xl[3 * i]; D.X[3 * i + 1] = y + D.xl[3 * i + 1]; D.X[3 * i + 2] = z + D.xl[3 * i + 2]; }
+    }
+}
+// pop()
+__global__ void __launch_bounds__(256) k_ba_restore(BADev D) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < D.nKF) D.pose[i] = D.poseBak[i];
+    if (i < D.nMP) { D.X[3 * i] = D.Xbak[3 * i]; D.X[3 * i + 1] = D.Xbak[3 * i + 1]; D.X[3 * i + 2] = D.Xbak[3 * i + 2]; }
 }
 
 // computeScale: sum_j x_j (lambda x_j + b_j); the pose part is added by rank 0 only (replicated), landmarks by their owner
-__global__ void __launch_bounds__(256) k_ba_scale(BADev D, double lambda) {
-    __shared__ double sh[8];
+__global__ void __launch_bounds__(256) k_ba_scale(BADev D, double lambda, double* out) {
+    __shared__ double sh[32];
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     double v = 0;
     if (i < D.n && D.rank == 0) v = D.xp[i] * (lambda * D.xp[i] + D.bpr[i]);
     const int j = i - D.n;
     if (j >= 0 && j < 3 * D.nMP) { const int l = j / 3; if (D.ptAct[l] && owned(D, l)) v = D.xl[j] * (lambda * D.xl[j] + D.bl[j]); }
-    const double s = block_sum(v, sh);
-    if (threadIdx.x == 0 && s != 0.0) atomicAdd(&D.scal[1], s);
+    double tot;
+    if (grid_sum(v, D.part, D.ticket, sh, &tot)) *out = tot;
 }
-
 
 // outlier test of src/Optimizer.cpp:384 / :411: chi2 of the LAST COMPUTED error (g2o keeps e->_error from the last
 // computeActiveErrors, which may belong to a rejected trial) or non-positive depth in the rig frame
@@ -359,172 +580,39 @@ __global__ void __launch_bounds__(256) k_ba_classify(BADev D, uint8_t* flag) {
     flag[e] = (chi > 5.991 || !(Xc[2] > 0.0)) ? 1 : 0;
 }
 
-// ------------------------------------------------------------------------------------------------- PoseOptimization
-// One CTA per frame; the whole schedule of src/Optimizer.cpp:138-181 (4 rounds x optimize(10), dense 6x6 LM) runs inside
-// the kernel. Block reductions of chi2 and of the 27 unique entries of (H,b); thread 0 does the 6x6 LDL^T and the LM logic.
-struct PoseOptArgs {
-    const int* offset; float* Tcw; const float* Xw; const float* kpxy; const float* invSigma2;
-    int faceW, faceH; uint8_t* outlier; int32_t* inliers; double* pose64; double* err; uint8_t* level;
-};
-
-__device__ double po_block_sum(double v, double* sh) {
-    const double s = block_sum(v, sh);
-    __shared__ double bc;
-    if (threadIdx.x == 0) bc = s;
-    __syncthreads();
-    const double r = bc;
-    __syncthreads();
-    return r;
-}
-
-__global__ void __launch_bounds__(256) k_pose_opt(PoseOptArgs A) {
-    __shared__ double sh[8];
-    __shared__ double Hs[27];
-    __shared__ Pose pose, pose0, backup;
-    __shared__ double x[6], lambda, ni;
-    __shared__ int ctrl;   // LM control word broadcast by thread 0
-    const int f = blockIdx.x, tid = threadIdx.x, T = blockDim.x;
-    const int beg = A.offset[f], n = A.offset[f + 1] - beg;
-    const double fc = A.faceW / 2.0;
-    const float dlt = (float)sqrt(5.991); const double delta = (double)dlt, dsqr = delta * delta;
-    if (tid == 0) { pose0 = pose_from_Tcw32(A.Tcw + 16 * f); pose = pose0; }
-    for (int i = tid; i < n; i += T) { A.outlier[beg + i] = 0; A.level[beg + i] = 0; A.err[2 * (beg + i)] = 0; A.err[2 * (beg + i) + 1] = 0; }
-    __syncthreads();
-    if (n < 3) { if (tid == 0) { A.inliers[f] = 0; if (A.pose64) { for (int i = 0; i < 3; i++) A.pose64[7 * f + i] = pose0.t[i]; for (int i = 0; i < 4; i++) A.pose64[7 * f + 3 + i] = pose0.q[i]; } } return; }
-    auto obs_face = [&](int e, double& mx, double& my, double& w) -> int {
-        const float kx = A.kpxy[2 * e], ky = A.kpxy[2 * e + 1];
-        const float fi = kx / (float)A.faceW, fj = ky / (float)A.faceH;
-        int face = -1;
-        if (fi >= 0 && fi < 1 && fj >= 1 && fj < 2) face = 1;
-        else if (fi >= 1 && fi < 2 && fj >= 0 && fj < 1) face = 3;
-        else if (fi >= 1 && fi < 2 && fj >= 1 && fj < 2) face = 0;
-        else if (fi >= 1 && fi < 2 && fj >= 2 && fj < 3) face = 4;
-        else if (fi >= 2 && fi < 3 && fj >= 1 && fj < 2) face = 2;
-        mx = (double)kx - floor((double)kx / A.faceW) * A.faceW; my = (double)ky - floor((double)ky / A.faceH) * A.faceH;
-        w = (double)A.invSigma2[e];
-        return face;
-    };
-    auto compute_errors = [&](bool robust, bool onlyActive) -> double {   // returns activeRobustChi2
-        double c = 0;
-        for (int i = tid; i < n; i += T) {
-            const int e = beg + i;
-            if (onlyActive && A.level[e] != 0) continue;
-            double mx, my, w; const int face = obs_face(e, mx, my, w);
-            const double Xw[3] = {(double)A.Xw[3 * e], (double)A.Xw[3 * e + 1], (double)A.Xw[3 * e + 2]};
-            double Xc[3], er[2];
-            pose_map(pose, Xw, Xc); edge_error(face, fc, mx, my, Xc, er);
-            A.err[2 * e] = er[0]; A.err[2 * e + 1] = er[1];
-            const double chi = w * (er[0] * er[0] + er[1] * er[1]);
-            if (robust) { double r0, r1; huber(delta, dsqr, chi, r0, r1); c += r0; } else c += chi;
-        }
-        return po_block_sum(c, sh);
-    };
-    int nBadEdges = 0;
-    bool robust = true;
-    for (int it = 0; it < 4; it++) {
-        if (tid == 0) pose = pose0;
-        __syncthreads();
-        int nAct = 0;
-        for (int i = tid; i < n; i += T) nAct += A.level[beg + i] == 0;
-        nAct = (int)po_block_sum((double)nAct, sh);
-        if (nAct > 0) {
-            int nBad = 0;
-            for (int iter = 0; iter < 10; iter++) {
-                double currentChi = compute_errors(robust, true);
-                const double iniChi = currentChi;
-                // buildSystem
-                double acc[27];
-                for (int k = 0; k < 27; k++) acc[k] = 0;
-                for (int i = tid; i < n; i += T) {
-                    const int e = beg + i;
-                    if (A.level[e] != 0) continue;
-                    double mx, my, w0; const int face = obs_face(e, mx, my, w0);
-                    const double Xw[3] = {(double)A.Xw[3 * e], (double)A.Xw[3 * e + 1], (double)A.Xw[3 * e + 2]};
-                    double Xc[3], G[2][3], Jp[2][6];
-                    pose_map(pose, Xw, Xc); edge_G(face, fc, Xc, G); edge_Jpose(G, Xc, Jp);
-                    const double e0 = A.err[2 * e], e1 = A.err[2 * e + 1];
-                    double rho1 = 1.0;
-                    if (robust) { double r0; huber(delta, dsqr, w0 * (e0 * e0 + e1 * e1), r0, rho1); }
-                    int k = 0;
-                    for (int a = 0; a < 6; a++) for (int b = a; b < 6; b++) acc[k++] += (rho1 * w0) * (Jp[0][a] * Jp[0][b] + Jp[1][a] * Jp[1][b]);
-                    for (int a = 0; a < 6; a++) acc[21 + a] -= rho1 * (Jp[0][a] * w0 * e0 + Jp[1][a] * w0 * e1);
-                }
-                for (int k = 0; k < 27; k++) { const double s = block_sum(acc[k], sh); if (tid == 0) Hs[k] = s; }
-                __syncthreads();
-                if (tid == 0 && iter == 0) {
-                    double m = 0; int k = 0;
-                    for (int a = 0; a < 6; a++) { m = fmax(m, fabs(Hs[k])); k += 6 - a; }
-                    lambda = 1e-5 * m; ni = 2; 
-                }
-                if (iter == 0) nBad = 0;
-                __syncthreads();
-                double rho = 0; int qmax = 0;
-                do {
-                    if (tid == 0) {
-                        backup = pose;
-                        double M[6][6], d[6], b[6]; int k = 0; bool ok = true;
-                        for (int a = 0; a < 6; a++) for (int c = a; c < 6; c++) { M[a][c] = Hs[k]; M[c][a] = Hs[k]; k++; }
-                        for (int a = 0; a < 6; a++) { M[a][a] += lambda; b[a] = Hs[21 + a]; }
-                        for (int j = 0; j < 6 && ok; j++) {   // LDL^T, LinearSolverDense: fails unless positive (LDLT::isPositive)
-                            double dj = M[j][j];
-                            for (int c = 0; c < j; c++) dj -= M[j][c] * M[j][c] * d[c];
-                            if (!(dj > 0.0) || !isfinite(dj)) { ok = false; break; }
-                            d[j] = dj;
-                            for (int i2 = j + 1; i2 < 6; i2++) { double s = M[i2][j]; for (int c = 0; c < j; c++) s -= M[i2][c] * M[j][c] * d[c]; M[i2][j] = s / dj; }
-                        }
-                        if (ok) {
-                            for (int i2 = 0; i2 < 6; i2++) { double s = b[i2]; for (int c = 0; c < i2; c++) s -= M[i2][c] * x[c]; x[i2] = s; }
-                            for (int i2 = 0; i2 < 6; i2++) x[i2] /= d[i2];
-                            for (int i2 = 5; i2 >= 0; i2--) { double s = x[i2]; for (int c = i2 + 1; c < 6; c++) s -= M[c][i2] * x[c]; x[i2] = s; }
-                            pose = pose_oplus(pose, x);
-                        } else { for (int i2 = 0; i2 < 6; i2++) x[i2] = 0; }
-                        ctrl = ok ? 1 : 0;
-                    }
-                    __syncthreads();
-                    const bool ok2 = ctrl != 0;
-                    double tempChi = compute_errors(robust, true);
-                    if (!ok2) tempChi = DBL_MAX;
-                    double scale = 0;
-                    for (int a = 0; a < 6; a++) scale += x[a] * (lambda * x[a] + Hs[21 + a]);
-                    scale += 1e-3;
-                    rho = (currentChi - tempChi) / scale;
-                    const bool good = rho > 0 && isfinite(tempChi);
-                    __syncthreads();
-                    if (tid == 0) {
-                        if (good) { double alpha = 1. - pow(2 * rho - 1, 3); alpha = fmin(alpha, 2. / 3.); lambda *= fmax(1. / 3., alpha); ni = 2; }
-                        else { lambda *= ni; ni *= 2; pose = backup; }
-                    }
-                    if (good) currentChi = tempChi;
-                    __syncthreads();
-                    qmax++;
-                } while (rho < 0 && qmax < 10);
-                if (qmax == 10 || rho == 0) break;
-                if ((iniChi - currentChi) * 1e3 < iniChi) nBad++; else nBad = 0;
-                if (nBad >= 3) break;
-            }
-        }
-        // classification (src/Optimizer.cpp:149-177): outliers get a fresh error, inliers keep the last computed one
-        int bad = 0;
-        for (int i = tid; i < n; i += T) {
-            const int e = beg + i;
-            double mx, my, w; const int face = obs_face(e, mx, my, w);
-            if (A.outlier[e]) {
-                const double Xw[3] = {(double)A.Xw[3 * e], (double)A.Xw[3 * e + 1], (double)A.Xw[3 * e + 2]};
-                double Xc[3], er[2];
-                pose_map(pose, Xw, Xc); edge_error(face, fc, mx, my, Xc, er);
-                A.err[2 * e] = er[0]; A.err[2 * e + 1] = er[1];
-            }
-            const float chi = (float)(w * (A.err[2 * e] * A.err[2 * e] + A.err[2 * e + 1] * A.err[2 * e + 1]));
-            if (chi > 5.991f) { A.outlier[e] = 1; A.level[e] = 1; bad++; } else { A.outlier[e] = 0; A.level[e] = 0; }
-        }
-        nBadEdges = (int)po_block_sum((double)bad, sh);
-        if (it == 2) robust = false;
-        if (n < 10) break;
+// ---------------------------------------------------------------------------------------------- one-shot NVLink all-reduce
+// Multi-GPU LocalBA: every rank owns an exchange buffer [payload doubles | flags] that all peers map (CUDA IPC). After the Schur
+// kernel has written the rank's partial [S | g | bpr | tail] into its own buffer, k_ba_xchg_signal publishes `epoch` in every peer's
+// flag slot for this rank (system-scope release); k_ba_xchg_reduce waits until all peers have published `epoch`, then every rank sums
+// the payloads of all ranks in rank order (identical result everywhere) into its private S / g / bpr / tail and adds lambda to the
+// diagonal. One 0.7 MB exchange per LM trial instead of five NCCL calls; a bounded spin turns a lost peer into an error, not a hang.
+struct XchgPeers { const double* payload[8]; volatile unsigned* flags[8]; int n, rank; };
+__global__ void k_ba_xchg_signal(XchgPeers P, unsigned epoch) {
+    if (threadIdx.x < P.n) {
+        __threadfence_system();
+        P.flags[threadIdx.x][P.rank] = epoch;   // slot `rank` of peer threadIdx.x's flag array
+        __threadfence_system();
     }
-    if (tid == 0) {
-        A.inliers[f] = n - nBadEdges;
-        pose_to_Tcw32(pose, A.Tcw + 16 * f);
-        if (A.pose64) { for (int i = 0; i < 3; i++) A.pose64[7 * f + i] = pose.t[i]; for (int i = 0; i < 4; i++) A.pose64[7 * f + 3 + i] = pose.q[i]; }
+}
+__global__ void __launch_bounds__(256) k_ba_xchg_reduce(XchgPeers P, unsigned epoch, double* dst, size_t count, int n, double lambda, int* err) {
+    __shared__ int ok;
+    if (threadIdx.x == 0) {
+        ok = 1;
+        volatile unsigned* mine = P.flags[P.rank];
+        for (int r = 0; r < P.n; r++) {
+            long long spins = 0;
+            while (mine[r] != epoch) { if (++spins > (1ll << 26)) { ok = 0; break; } __nanosleep(64); }
+            if (!ok) break;
+        }
+        __threadfence_system();
+    }
+    __syncthreads();
+    if (!ok) { if (threadIdx.x == 0) *err = 1; return; }
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += (size_t)gridDim.x * blockDim.x) {
+        double s = 0;
+        for (int r = 0; r < P.n; r++) s += __ldcv(P.payload[r] + i);
+        if (i < (size_t)n * n && (i / n) == (i % n)) s += lambda;
+        dst[i] = s;
     }
 }
 
@@ -535,7 +623,6 @@ using namespace cslam;
 
 // ---- NCCL through dlopen (libnccl.so.2 is already mapped when torch.distributed is in use); no link-time dependency
 typedef struct { char internal[128]; } nccl_uid_t;
-typedef void* nccl_comm_t;
 struct NcclApi {
     void* h = nullptr;
     int (*GetUniqueId)(nccl_uid_t*) = nullptr;
@@ -561,18 +648,7 @@ static NcclApi* nccl_api() {
     if (!api.GetUniqueId || !api.CommInitRank || !api.AllReduce || !api.CommDestroy) { dlclose(api.h); api.h = nullptr; return nullptr; }
     return &api;
 }
-enum { NCCL_F64 = 8, NCCL_SUM = 0, NCCL_MAX = 2 };
-
-struct cslam_optimizer {
-    int device = 0;
-    cudaStream_t stream = nullptr;
-    nccl_comm_t comm = nullptr; int rank = 0, nranks = 1;
-    int64_t launches = 0;
-    // device arena: chunks are kept across calls (cudaMalloc/cudaFree per BA call cost more than the solve itself)
-    struct Chunk { char* p; size_t size, used; };
-    std::vector<Chunk> chunks;
-    double* h_scal = nullptr;  // pinned
-};
+enum { NCCL_U8 = 1, NCCL_F64 = 8, NCCL_SUM = 0, NCCL_MAX = 2 };
 
 extern "C" int cslam_optimizer_create(cslam_optimizer** out, int device) {
     if (!out) return CSLAM_E_BADARG;
@@ -581,21 +657,21 @@ extern "C" int cslam_optimizer_create(cslam_optimizer** out, int device) {
     if (device < 0 || device >= ndev) { set_error("device %d out of range", device); return CSLAM_E_BADARG; }
     CSLAM_CUDA(cudaSetDevice(device));
     cslam_optimizer* o = new cslam_optimizer; o->device = device;
-    if (cudaStreamCreateWithFlags(&o->stream, cudaStreamNonBlocking) != cudaSuccess || cudaMallocHost(&o->h_scal, 8 * sizeof(double)) != cudaSuccess) {
+    if (cudaStreamCreateWithFlags(&o->stream, cudaStreamNonBlocking) != cudaSuccess || cudaMallocHost(&o->h_scal, 16 * sizeof(double)) != cudaSuccess) {
         set_error("optimizer: stream / pinned allocation failed"); delete o; return CSLAM_E_CUDA;
     }
-    cudaFuncSetAttribute(k_ba_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    cudaFuncSetAttribute(k_ba_schur, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    cudaFuncSetAttribute(k_ba_linearize, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+    if (const char* e = getenv("CSLAM_SOLVE_CLUSTER")) o->clusterSize = std::max(1, std::min(atoi(e), 16));
+    if (o->clusterSize > 8) cudaFuncSetAttribute(k_ba_solve, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+    cudaFuncSetAttribute(k_ba_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024);
     *out = o;
     return CSLAM_OK;
 }
-static void free_pool(cslam_optimizer* o) { for (auto& c : o->chunks) c.used = 0; }
 static void release_pool(cslam_optimizer* o) { for (auto& c : o->chunks) cudaFree(c.p); o->chunks.clear(); }
 extern "C" void cslam_optimizer_destroy(cslam_optimizer* o) {
     if (!o) return;
     cudaSetDevice(o->device);
     if (o->stream) cudaStreamSynchronize(o->stream);
+    for (auto& p : o->peers) { if (p.base && !p.mine) cudaIpcCloseMemHandle(p.base); else if (p.base) cudaFree(p.base); }
     release_pool(o);
     if (o->comm && nccl_api()) nccl_api()->CommDestroy(o->comm);
     if (o->stream) cudaStreamDestroy(o->stream);
@@ -612,6 +688,51 @@ extern "C" int cslam_nccl_unique_id(uint8_t id128[128]) {
     std::memcpy(id128, id.internal, 128);
     return CSLAM_OK;
 }
+
+// Exchange buffers of the one-shot all-reduce: allocate, publish the CUDA IPC handle through ncclAllGather, map every peer.
+static const size_t XCHG_FLAG_BYTES = 256;
+static int setup_xchg(cslam_optimizer* o, size_t payloadBytes) {
+    NcclApi* a = nccl_api();
+    if (o->nranks > 8 || !a->AllGather) return 1;   // fall back to NCCL
+    for (auto& p : o->peers) { if (p.base && !p.mine) cudaIpcCloseMemHandle(p.base); else if (p.base) cudaFree(p.base); }
+    o->peers.assign(o->nranks, cslam_optimizer::Peer());
+    void* mine = nullptr;
+    const size_t bytes = ((payloadBytes + 255) & ~(size_t)255) + XCHG_FLAG_BYTES;
+    CSLAM_CUDA(cudaMalloc(&mine, bytes));
+    CSLAM_CUDA(cudaMemset(mine, 0, bytes));
+    cudaIpcMemHandle_t h;
+    CSLAM_CUDA(cudaIpcGetMemHandle(&h, mine));
+    cudaIpcMemHandle_t* dAll = nullptr;
+    CSLAM_CUDA(cudaMalloc((void**)&dAll, sizeof(h) * o->nranks));
+    CSLAM_CUDA(cudaMemcpy(dAll + o->rank, &h, sizeof(h), cudaMemcpyHostToDevice));
+    int rc = a->AllGather(dAll + o->rank, dAll, sizeof(h), NCCL_U8, o->comm, o->stream);
+    if (rc) { set_error("ncclAllGather (IPC handles) failed (%d)", rc); return CSLAM_E_NCCL; }
+    std::vector<cudaIpcMemHandle_t> all(o->nranks);
+    CSLAM_CUDA(cudaMemcpyAsync(all.data(), dAll, sizeof(h) * o->nranks, cudaMemcpyDeviceToHost, o->stream));
+    CSLAM_CUDA(cudaStreamSynchronize(o->stream));
+    cudaFree(dAll);
+    bool ok = true;
+    for (int r = 0; r < o->nranks; r++) {
+        if (r == o->rank) { o->peers[r].base = mine; o->peers[r].mine = true; continue; }
+        void* p = nullptr;
+        if (cudaIpcOpenMemHandle(&p, all[r], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { cudaGetLastError(); ok = false; break; }
+        o->peers[r].base = p;
+    }
+    // all ranks must agree on the path
+    double* flag = nullptr;
+    CSLAM_CUDA(cudaMalloc((void**)&flag, 8));
+    const double v = ok ? 0.0 : 1.0;
+    CSLAM_CUDA(cudaMemcpy(flag, &v, 8, cudaMemcpyHostToDevice));
+    rc = a->AllReduce(flag, flag, 1, NCCL_F64, NCCL_SUM, o->comm, o->stream);
+    double bad = 1;
+    CSLAM_CUDA(cudaMemcpyAsync(&bad, flag, 8, cudaMemcpyDeviceToHost, o->stream));
+    CSLAM_CUDA(cudaStreamSynchronize(o->stream));
+    cudaFree(flag);
+    if (rc || bad != 0.0) return 1;
+    o->xchgBytes = payloadBytes; o->oneShot = true; o->epoch = 0;
+    return 0;
+}
+
 extern "C" int cslam_optimizer_init_nccl(cslam_optimizer* o, const uint8_t id128[128], int rank, int nranks) {
     if (!o || !id128 || nranks < 1 || rank < 0 || rank >= nranks) return CSLAM_E_BADARG;
     NcclApi* a = nccl_api();
@@ -624,39 +745,23 @@ extern "C" int cslam_optimizer_init_nccl(cslam_optimizer* o, const uint8_t id128
     return CSLAM_OK;
 }
 
-template <class T>
-static int dalloc(cslam_optimizer* o, T** p, size_t count, bool zero = false) {
-    const size_t bytes = (std::max<size_t>(count, 1) * sizeof(T) + 255) & ~(size_t)255;
-    char* q = nullptr;
-    for (auto& c : o->chunks) if (c.size - c.used >= bytes) { q = c.p + c.used; c.used += bytes; break; }
-    if (!q) {
-        cslam_optimizer::Chunk c; c.size = std::max<size_t>(bytes, (size_t)64 << 20); c.used = bytes;
-        CSLAM_CUDA(cudaMalloc((void**)&c.p, c.size));
-        o->chunks.push_back(c); q = c.p;
-    }
-    if (zero) CSLAM_CUDA(cudaMemsetAsync(q, 0, bytes, o->stream));
-    *p = (T*)q;
-    return 0;
-}
-template <class T>
-static int dupload(cslam_optimizer* o, const T** p, const std::vector<T>& v) {
-    T* q = nullptr; int rc = dalloc(o, &q, v.size());
-    if (rc) return rc;
-    if (!v.empty()) CSLAM_CUDA(cudaMemcpyAsync(q, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice, o->stream));
-    *p = q;
-    return 0;
-}
-
 namespace {
 struct BAHost {
     cslam_optimizer* o; BADev D; cslam_ba_result* res;
     std::vector<int> perm;            // sorted edge position -> caller's edge index
     std::vector<uint8_t> level; std::vector<int> poseIdx; std::vector<uint8_t> ptAct, fixed;
     int* d_poseIdx = nullptr; uint8_t* d_ptAct = nullptr; uint8_t* d_flag = nullptr;
+    double* Lt = nullptr; double* LDt = nullptr; int ldp = 0;
+    double* red = nullptr;            // private reduce buffer [S | g | bpr | tail]
+    double* xmine = nullptr;          // this rank's exchange payload (one-shot path) - the Schur kernel writes there
+    int* d_xerr = nullptr;
     double lambda = -1, ni = 2; int nBad = 0; int iterations = 0, trials = 0;
     const volatile uint8_t* stop = nullptr;
+    std::vector<int> h_eMP, h_eKF; int nActive = 0;
+    bool useOneShot = false;
     bool terminate() const { return stop ? (*stop != 0) : false; }
-    int grid(int n) const { return std::max(1, cdiv(n, 256)); }
+    int grid(int n, int t = 256) const { return std::max(1, cdiv(n, t)); }
+    size_t payload() const { return (size_t)D.n * D.n + 2 * (size_t)D.n + 4; }
 
     int allreduce(double* buf, size_t count, int op) {
         if (o->nranks <= 1) return 0;
@@ -664,12 +769,16 @@ struct BAHost {
         if (rc) { set_error("ncclAllReduce failed (%d)", rc); return CSLAM_E_NCCL; }
         return 0;
     }
-    int fetch_scal() {   // device scal[0..3] -> host (with the cross-rank reductions the quantities need)
-        CSLAM_CUDA(cudaMemcpyAsync(o->h_scal, D.scal, 4 * sizeof(double), cudaMemcpyDeviceToHost, o->stream));
+    int fetch(const double* src, int count) {
+        CSLAM_CUDA(cudaMemcpyAsync(o->h_scal, src, count * sizeof(double), cudaMemcpyDeviceToHost, o->stream));
         CSLAM_CUDA(cudaStreamSynchronize(o->stream));
         return 0;
     }
-    int zero_scal(int i, int n) { CSLAM_CUDA(cudaMemsetAsync(D.scal + i, 0, n * sizeof(double), o->stream)); return 0; }
+    void bind() {   // partial system of this rank goes to `w` (exchange payload on the one-shot path), the reduced one lives in `red`
+        double* w = (o->nranks > 1 && useOneShot) ? xmine : red;
+        D.S = w; D.g = w + (size_t)D.n * D.n; D.bpr = D.g + D.n; D.tail = D.bpr + D.n;
+    }
+    BADev reducedView() const { BADev R = D; R.S = red; R.g = red + (size_t)D.n * D.n; R.bpr = R.g + D.n; R.tail = R.bpr + D.n; return R; }
 
     // initializeOptimization(level 0): active edges, active vertices, compact pose indices (sparse_optimizer.cpp:206-267,166-190)
     int initialize() {
@@ -684,61 +793,73 @@ struct BAHost {
         CSLAM_CUDA(cudaMemcpyAsync(d_ptAct, ptAct.data(), D.nMP, cudaMemcpyHostToDevice, o->stream));
         CSLAM_CUDA(cudaMemcpyAsync(D.level, level.data(), D.nE, cudaMemcpyHostToDevice, o->stream));
         nActive = 0; for (int e = 0; e < D.nE; e++) nActive += level[e] == 0;
+        bind();
         return 0;
     }
-    std::vector<int> h_eMP, h_eKF; int nActive = 0;
-
     int errors_chi2(double* chi) {   // computeActiveErrors + activeRobustChi2
-        int rc = zero_scal(0, 1); if (rc) return rc;
-        k_ba_errors<<<grid(D.nE), 256, 0, o->stream>>>(D); o->launches++;
+        k_ba_errors<<<grid(D.nE), 256, 0, o->stream>>>(D, D.scal); o->launches++;
+        int rc;
         if ((rc = allreduce(D.scal, 1, NCCL_SUM))) return rc;
-        if ((rc = fetch_scal())) return rc;
+        if ((rc = fetch(D.scal, 1))) return rc;
         *chi = o->h_scal[0];
         return 0;
     }
     int build_system() {
-        CSLAM_CUDA(cudaMemsetAsync(D.Hpp, 0, (size_t)std::max(D.nP, 1) * 36 * 8, o->stream));
-        CSLAM_CUDA(cudaMemsetAsync(D.bp, 0, (size_t)std::max(D.nP, 1) * 6 * 8, o->stream));
-        CSLAM_CUDA(cudaMemsetAsync(D.Hll, 0, (size_t)D.nMP * 9 * 8, o->stream));
-        CSLAM_CUDA(cudaMemsetAsync(D.bl, 0, (size_t)D.nMP * 3 * 8, o->stream));
-        const int useSmem = D.nP > 0 && D.nP <= 160;
-        k_ba_linearize<<<grid(D.nE), 256, useSmem ? (size_t)D.nP * 42 * 8 : 0, o->stream>>>(D, useSmem); o->launches++;
+        k_ba_lin_points<<<grid(D.nMP, 128), 128, 0, o->stream>>>(D); o->launches++;
+        if (D.nQ > 0) { k_ba_lin_poses<<<D.nQ, 256, 0, o->stream>>>(D); o->launches++; }
         CSLAM_CUDA(cudaGetLastError());
-        // landmark sharding: every rank linearised only the edges of its own landmarks -> the pose blocks are partial sums
-        int rc;
-        if ((rc = allreduce(D.Hpp, (size_t)D.nP * 36, NCCL_SUM)) || (rc = allreduce(D.bp, (size_t)D.nP * 6, NCCL_SUM))) return rc;
         return 0;
     }
     int lambda_init(double* lam) {
-        int rc = zero_scal(2, 1); if (rc) return rc;
-        k_ba_maxdiag<<<grid(D.nP * 6 + D.nMP * 3), 256, 0, o->stream>>>(D); o->launches++;   // poses: full Hpp (see build_system); landmarks: own
+        int rc;
+        CSLAM_CUDA(cudaMemsetAsync(D.scal + 2, 0, sizeof(double), o->stream));
+        if (o->nranks > 1 && D.nP > 0) {   // computeLambdaInit needs the full pose blocks: sum the partial diagonals once per optimize()
+            if ((rc = allreduce(D.Hpp, (size_t)D.nP * 36, NCCL_SUM))) return rc;
+        }
+        k_ba_maxdiag<<<grid(D.nP * 6 + D.nMP * 3), 256, 0, o->stream>>>(D); o->launches++;
         if ((rc = allreduce(D.scal + 2, 1, NCCL_MAX))) return rc;
-        if ((rc = fetch_scal())) return rc;
+        if ((rc = fetch(D.scal, 4))) return rc;
         *lam = 1e-5 * o->h_scal[2];
         return 0;
     }
-    // one LM trial's linear solve (BlockSolver::solve): returns ok flag
-    int solve(bool* ok) {
+    // one LM trial's linear solve (BlockSolver::solve)
+    int solve() {
         int rc;
         k_ba_dinv<<<grid(D.nMP), 256, 0, o->stream>>>(D, lambda); o->launches++;
         if (D.n > 0) {
-            // Hpp / bp are already full sums on every rank: rank 0 alone seeds [S | g | bpr] with them, the others start from 0
-            if (o->rank == 0) { k_ba_s_init<<<grid(D.n * D.n), 256, 0, o->stream>>>(D); o->launches++; }
-            else CSLAM_CUDA(cudaMemsetAsync(D.S, 0, ((size_t)D.n * D.n + 2 * D.n) * 8, o->stream));
-            const int chunks = 16;
-            k_ba_schur<<<dim3(chunks, D.nKF), 256, (size_t)(6 * D.n + 6) * 8, o->stream>>>(D, chunks); o->launches++;
-            if ((rc = allreduce(D.S, (size_t)D.n * D.n + 2 * D.n, NCCL_SUM))) return rc;
-            k_ba_add_lambda<<<grid(D.n), 256, 0, o->stream>>>(D, lambda); o->launches++;
-            if ((rc = zero_scal(3, 1))) return rc;
-            const size_t smem = (2 * (size_t)(D.n + 1) * (LD_NB + 1) + 2 * D.n) * 8;
-            if (smem > 200 * 1024) { set_error("reduced camera system too large for the single-CTA solver (n=%d)", D.n); return CSLAM_E_CAPACITY; }
-            k_ba_solve<<<1, 1024, smem, o->stream>>>(D); o->launches++;
+            const bool multi = o->nranks > 1;
+            k_ba_schur<<<dim3(D.nQ, D.nQ), SCHUR_T, 0, o->stream>>>(D, multi ? 0.0 : lambda); o->launches++;
+            BADev R = D;
+            if (multi) {
+                R = reducedView();
+                if (useOneShot) {
+                    XchgPeers P; P.n = o->nranks; P.rank = o->rank;
+                    const size_t off = (o->xchgBytes + 255) & ~(size_t)255;
+                    for (int r = 0; r < o->nranks; r++) { P.payload[r] = (const double*)o->peers[r].base; P.flags[r] = (volatile unsigned*)((char*)o->peers[r].base + off); }
+                    const unsigned ep = ++o->epoch;
+                    k_ba_xchg_signal<<<1, 32, 0, o->stream>>>(P, ep); o->launches++;
+                    k_ba_xchg_reduce<<<std::min(148, grid((int)std::min<size_t>(payload(), 1u << 30))), 256, 0, o->stream>>>(P, ep, red, payload(), D.n, lambda, d_xerr); o->launches++;
+                } else {
+                    CSLAM_CUDA(cudaMemcpyAsync(red, D.S, payload() * 8, cudaMemcpyDeviceToDevice, o->stream));
+                    if ((rc = allreduce(red, payload(), NCCL_SUM))) return rc;
+                    k_ba_add_lambda_launch(R);
+                }
+            }
+            CSLAM_CUDA(cudaMemsetAsync(D.scal + 3, 0, sizeof(double), o->stream));
+            cudaLaunchConfig_t cfg = {};
+            cfg.gridDim = dim3(o->clusterSize); cfg.blockDim = dim3(SOLVE_T); cfg.dynamicSmemBytes = (size_t)D.n * 8; cfg.stream = o->stream;
+            cudaLaunchAttribute at[1];
+            at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = o->clusterSize; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+            cfg.attrs = at; cfg.numAttrs = 1;
+            CSLAM_CUDA(cudaLaunchKernelEx(&cfg, k_ba_solve, R, Lt, LDt, ldp)); o->launches++;
+            solvedView = R;
         }
-        k_ba_backsub<<<grid(D.nMP), 256, 0, o->stream>>>(D); o->launches++;
+        k_ba_backsub<<<grid(D.nMP, 128), 128, 0, o->stream>>>(D); o->launches++;
         CSLAM_CUDA(cudaGetLastError());
-        *ok = true;   // the flag itself is read together with chi2/scale after the update (one D2H per trial)
         return 0;
     }
+    BADev solvedView;
+    void k_ba_add_lambda_launch(const BADev& R);
     // OptimizationAlgorithmLevenberg::solve ; result 0 OK, 1 Terminate
     int lm_iteration(int iteration, int* result) {
         int rc; double currentChi = 0;
@@ -748,18 +869,15 @@ struct BAHost {
         if (iteration == 0) { if ((rc = lambda_init(&lambda))) return rc; ni = 2; nBad = 0; }
         double rho = 0; int qmax = 0; int accepted = 0;
         do {
-            CSLAM_CUDA(cudaMemcpyAsync(D.poseBak, D.pose, D.nKF * sizeof(Pose), cudaMemcpyDeviceToDevice, o->stream));
-            CSLAM_CUDA(cudaMemcpyAsync(D.Xbak, D.X, (size_t)D.nMP * 3 * 8, cudaMemcpyDeviceToDevice, o->stream));
-            bool ok2 = true;
-            if ((rc = solve(&ok2))) return rc;
+            if ((rc = solve())) return rc;
             k_ba_update<<<grid(std::max(D.nKF, D.nMP)), 256, 0, o->stream>>>(D); o->launches++;
-            if ((rc = zero_scal(0, 2))) return rc;
-            k_ba_errors<<<grid(D.nE), 256, 0, o->stream>>>(D); o->launches++;
-            k_ba_scale<<<grid(D.n + 3 * D.nMP), 256, 0, o->stream>>>(D, lambda); o->launches++;
+            k_ba_errors<<<grid(D.nE), 256, 0, o->stream>>>(D, D.scal); o->launches++;
+            BADev SV = D; if (D.n > 0 && o->nranks > 1) { SV.bpr = solvedView.bpr; }
+            k_ba_scale<<<grid(D.n + 3 * D.nMP), 256, 0, o->stream>>>(SV, lambda, D.scal + 1); o->launches++;
             if ((rc = allreduce(D.scal, 2, NCCL_SUM))) return rc;
-            if ((rc = fetch_scal())) return rc;
+            if ((rc = fetch(D.scal, 4))) return rc;
             tempChi = o->h_scal[0];
-            ok2 = o->h_scal[3] == 0.0;
+            bool ok2 = o->h_scal[3] == 0.0;
             trials++;
             if (!ok2) tempChi = DBL_MAX;
             rho = currentChi - tempChi;
@@ -771,8 +889,7 @@ struct BAHost {
                 lambda *= std::max(1. / 3., alpha); ni = 2; currentChi = tempChi; accepted = 1;
             } else {
                 lambda *= ni; ni *= 2;
-                CSLAM_CUDA(cudaMemcpyAsync(D.pose, D.poseBak, D.nKF * sizeof(Pose), cudaMemcpyDeviceToDevice, o->stream));
-                CSLAM_CUDA(cudaMemcpyAsync(D.X, D.Xbak, (size_t)D.nMP * 3 * 8, cudaMemcpyDeviceToDevice, o->stream));
+                k_ba_restore<<<grid(std::max(D.nKF, D.nMP)), 256, 0, o->stream>>>(D); o->launches++;
                 if (!ok2) rho = -1;
             }
             qmax++;
@@ -791,27 +908,41 @@ struct BAHost {
         if (nActive == 0) return 0;   // g2o: "0 vertices to optimize"
         int result = 0;
         for (int i = 0; i < its && !terminate() && result == 0; i++) { int rc = lm_iteration(i, &result); if (rc) return rc; }
+        if (o->nranks > 1 && useOneShot) {
+            int xe = 0;
+            CSLAM_CUDA(cudaMemcpyAsync(&xe, d_xerr, sizeof(int), cudaMemcpyDeviceToHost, o->stream));
+            CSLAM_CUDA(cudaStreamSynchronize(o->stream));
+            if (xe) { set_error("one-shot all-reduce: a peer never signalled (timeout)"); return CSLAM_E_NCCL; }
+        }
         return 0;
     }
-    double* d_flag64 = nullptr;
     int classify(std::vector<uint8_t>& flags) {
         k_ba_classify<<<grid(D.nE), 256, 0, o->stream>>>(D, d_flag); o->launches++;
         flags.resize(D.nE);
         CSLAM_CUDA(cudaMemcpyAsync(flags.data(), d_flag, D.nE, cudaMemcpyDeviceToHost, o->stream));
         CSLAM_CUDA(cudaStreamSynchronize(o->stream));
-        if (o->nranks > 1) {   // a rank only holds valid errors / points for the edges of its own landmarks: combine the owners' flags
-            std::vector<double> fl(D.nE);
-            for (int s = 0; s < D.nE; s++) fl[s] = ((h_eMP[s] % o->nranks) == o->rank && flags[s]) ? 1.0 : 0.0;
-            CSLAM_CUDA(cudaMemcpyAsync(d_flag64, fl.data(), (size_t)D.nE * 8, cudaMemcpyHostToDevice, o->stream));
-            int rc = allreduce(d_flag64, D.nE, NCCL_SUM);
-            if (rc) return rc;
-            CSLAM_CUDA(cudaMemcpyAsync(fl.data(), d_flag64, (size_t)D.nE * 8, cudaMemcpyDeviceToHost, o->stream));
+        if (o->nranks > 1) {   // a rank only holds valid errors / points for the edges of its own landmarks: keep the owners' flags (max over ranks)
+            for (int s = 0; s < D.nE; s++) if ((h_eMP[s] % o->nranks) != o->rank) flags[s] = 0;
+            CSLAM_CUDA(cudaMemcpyAsync(d_flag, flags.data(), D.nE, cudaMemcpyHostToDevice, o->stream));
+            int rc = nccl_api()->AllReduce(d_flag, d_flag, D.nE, NCCL_U8, NCCL_MAX, o->comm, o->stream);
+            if (rc) { set_error("ncclAllReduce (flags) failed (%d)", rc); return CSLAM_E_NCCL; }
+            CSLAM_CUDA(cudaMemcpyAsync(flags.data(), d_flag, D.nE, cudaMemcpyDeviceToHost, o->stream));
             CSLAM_CUDA(cudaStreamSynchronize(o->stream));
-            for (int s = 0; s < D.nE; s++) flags[s] = fl[s] != 0.0;
         }
         return 0;
     }
 };
+__global__ void __launch_bounds__(256) k_ba_add_lambda(double* S, int n, double lambda) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) S[(size_t)i * n + i] += lambda;
+}
+void BAHost::k_ba_add_lambda_launch(const BADev& R) { k_ba_add_lambda<<<grid(R.n), 256, 0, o->stream>>>(R.S, R.n, lambda); o->launches++; }
+
+// non-owner points are stale on a rank: every point is taken from its owner (sum of owner ? X : 0)
+__global__ void __launch_bounds__(256) k_ba_mask_points(BADev D) {
+    const int l = blockIdx.x * blockDim.x + threadIdx.x;
+    if (l < D.nMP && !owned(D, l)) { D.X[3 * l] = 0; D.X[3 * l + 1] = 0; D.X[3 * l + 2] = 0; }
+}
 }  // namespace
 
 extern "C" int cslam_local_ba(cslam_optimizer* o, cslam_ba_problem* p, const volatile uint8_t* stop_flag, int its1, int its2, cslam_ba_result* r) {
@@ -864,25 +995,54 @@ extern "C" int cslam_local_ba(cslam_optimizer* o, cslam_ba_problem* p, const vol
     std::vector<double> X((size_t)nMP * 3);
     for (size_t i = 0; i < X.size(); i++) X[i] = (double)p->points[i];
     H.fixed.assign(p->kf_fixed, p->kf_fixed + nKF); H.level.assign(nE, 0); H.poseIdx.assign(nKF, -1); H.ptAct.assign(nMP, 0);
+    std::vector<int> kfOfQ;
+    for (int k = 0; k < nKF; k++) if (!H.fixed[k]) kfOfQ.push_back(k);
+    const int nQ = (int)kfOfQ.size();
+    D.nQ = nQ;
     int rc;
-    const int nPmax = nKF, nmax = 6 * nPmax;
+    const int nmax = 6 * nQ;
     const Pose* cpose = nullptr; const double* cX = nullptr;
     if ((rc = dupload(o, &cpose, poses)) || (rc = dupload(o, &cX, X)) || (rc = dupload(o, &D.eMP, H.h_eMP)) || (rc = dupload(o, &D.eKF, H.h_eKF)) ||
         (rc = dupload(o, &D.obs, obs)) || (rc = dupload(o, &D.face, face)) || (rc = dupload(o, &D.lmStart, lmStart)) || (rc = dupload(o, &D.peStart, peStart)) ||
-        (rc = dupload(o, &D.peList, peList))) return rc;
+        (rc = dupload(o, &D.peList, peList)) || (rc = dupload(o, &D.kfOfQ, kfOfQ))) return rc;
     D.pose = const_cast<Pose*>(cpose); D.X = const_cast<double*>(cX);
-    double* red = nullptr;
-    if ((rc = dalloc(o, &D.poseBak, nKF)) || (rc = dalloc(o, &D.Xbak, (size_t)nMP * 3)) || (rc = dalloc(o, &D.err, (size_t)nE * 2, true)) || (rc = dalloc(o, &D.level, nE)) ||
-        (rc = dalloc(o, &H.d_poseIdx, nKF)) || (rc = dalloc(o, &H.d_ptAct, nMP)) || (rc = dalloc(o, &H.d_flag, nE)) || (rc = dalloc(o, &D.Hpp, (size_t)nPmax * 36)) ||
-        (rc = dalloc(o, &D.bp, (size_t)nPmax * 6)) || (rc = dalloc(o, &D.Hll, (size_t)nMP * 9)) || (rc = dalloc(o, &D.bl, (size_t)nMP * 3)) ||
+    H.ldp = ((nmax + 1 + 8) + 3) & ~3;
+    const size_t payloadMax = (size_t)nmax * nmax + 2 * (size_t)nmax + 4;
+    const int maxBlocks = std::max({cdiv(nE, 256), cdiv(nmax + 3 * nMP, 256), 1});
+    long long* pairCnt = nullptr;
+    if ((rc = dalloc(o, &D.poseBak, nKF)) || (rc = dalloc(o, &D.Xbak, (size_t)nMP * 3)) || (rc = dalloc(o, &D.err, (size_t)nE * 2, true)) || (rc = dalloc(o, &D.level, nE, true)) ||
+        (rc = dalloc(o, &H.d_poseIdx, nKF)) || (rc = dalloc(o, &H.d_ptAct, nMP)) || (rc = dalloc(o, &H.d_flag, nE)) || (rc = dalloc(o, &D.Hpp, (size_t)std::max(nQ, 1) * 36)) ||
+        (rc = dalloc(o, &D.bp, (size_t)std::max(nQ, 1) * 6)) || (rc = dalloc(o, &D.Hll, (size_t)nMP * 9)) || (rc = dalloc(o, &D.bl, (size_t)nMP * 3)) ||
         (rc = dalloc(o, &D.Hpl, (size_t)nE * 18)) || (rc = dalloc(o, &D.Dinv, (size_t)nMP * 9)) || (rc = dalloc(o, &D.db, (size_t)nMP * 3)) ||
-        (rc = dalloc(o, &red, (size_t)nmax * nmax + 2 * nmax)) || (rc = dalloc(o, &D.xp, nmax, true)) || (rc = dalloc(o, &D.xl, (size_t)nMP * 3, true)) ||
-        (rc = dalloc(o, &D.scal, 8, true)) || (rc = dalloc(o, &H.d_flag64, o->nranks > 1 ? nE : 1))) return rc;
+        (rc = dalloc(o, &H.red, payloadMax)) || (rc = dalloc(o, &D.xp, std::max(nmax, 1), true)) || (rc = dalloc(o, &D.xl, (size_t)nMP * 3, true)) ||
+        (rc = dalloc(o, &D.scal, 8, true)) || (rc = dalloc(o, &D.part, maxBlocks)) || (rc = dalloc(o, &D.ticket, 4, true)) ||
+        (rc = dalloc(o, &H.Lt, (size_t)LD_NB * H.ldp)) || (rc = dalloc(o, &H.LDt, (size_t)LD_NB * H.ldp)) || (rc = dalloc(o, &pairCnt, (size_t)nQ * nQ + 1)) ||
+        (rc = dalloc(o, &H.d_xerr, 1, true))) return rc;
     D.poseIdx = H.d_poseIdx; D.ptAct = H.d_ptAct;
-    auto bind_reduce = [&]() { D.S = red; D.g = red + (size_t)D.n * D.n; D.bpr = D.g + D.n; };
+    // ---- multi-GPU exchange path
+    if (o->nranks > 1) {
+        if (!getenv("CSLAM_BA_NCCL_ONLY") && (!o->oneShot || o->xchgBytes < payloadMax * 8)) {
+            const int xr = setup_xchg(o, payloadMax * 8);
+            if (xr < 0) return xr;
+        }
+        H.useOneShot = o->oneShot && o->xchgBytes >= payloadMax * 8 && !getenv("CSLAM_BA_NCCL_ONLY");
+        if (H.useOneShot) H.xmine = (double*)o->peers[o->rank].base;
+    }
+    // ---- co-observation lists (once per call, all edges)
+    if (nQ > 0) {
+        k_ba_pairs_count<<<dim3(nQ, nQ), 128, 0, o->stream>>>(D, pairCnt); o->launches++;
+        k_ba_pairs_scan<<<1, 1024, 0, o->stream>>>(pairCnt, nQ * nQ); o->launches++;
+        long long total = 0;
+        CSLAM_CUDA(cudaMemcpyAsync(&total, pairCnt + (size_t)nQ * nQ, sizeof(long long), cudaMemcpyDeviceToHost, o->stream));
+        CSLAM_CUDA(cudaStreamSynchronize(o->stream));
+        int2* tuples = nullptr;
+        if ((rc = dalloc(o, &tuples, (size_t)std::max<long long>(total, 1)))) return rc;
+        k_ba_pairs_fill<<<dim3(nQ, nQ), 128, 0, o->stream>>>(D, pairCnt, tuples); o->launches++;
+        CSLAM_CUDA(cudaGetLastError());
+        D.pairStart = pairCnt; D.tuples = tuples;
+    }
     // ---- src/Optimizer.cpp:363-395
     if ((rc = H.initialize())) return rc;
-    bind_reduce();
     if ((rc = H.optimize(its1))) return rc;
     std::vector<uint8_t> flags;
     if (!H.terminate()) {
@@ -890,18 +1050,12 @@ extern "C" int cslam_local_ba(cslam_optimizer* o, cslam_ba_problem* p, const vol
         for (int s = 0; s < nE; s++) if (flags[s]) H.level[s] = 1;
         D.robust = 0;
         if ((rc = H.initialize())) return rc;
-        bind_reduce();
         if ((rc = H.optimize(its2))) return rc;
     }
     if ((rc = H.classify(flags))) return rc;
     // ---- write back (src/Optimizer.cpp:432-450): float32 poses / points; with landmark sharding every rank holds its own points
     if (o->nranks > 1) {
-        // non-owned points were never touched; owners' values are combined with a sum of (owner ? X : 0)
-        std::vector<double> Xh((size_t)nMP * 3);
-        CSLAM_CUDA(cudaMemcpyAsync(Xh.data(), D.X, Xh.size() * 8, cudaMemcpyDeviceToHost, o->stream));
-        CSLAM_CUDA(cudaStreamSynchronize(o->stream));
-        for (int l = 0; l < nMP; l++) if ((l % o->nranks) != o->rank) { Xh[3 * l] = 0; Xh[3 * l + 1] = 0; Xh[3 * l + 2] = 0; }
-        CSLAM_CUDA(cudaMemcpyAsync(D.X, Xh.data(), Xh.size() * 8, cudaMemcpyHostToDevice, o->stream));
+        k_ba_mask_points<<<H.grid(nMP), 256, 0, o->stream>>>(D); o->launches++;
         if ((rc = H.allreduce(D.X, (size_t)nMP * 3, NCCL_SUM))) return rc;
     }
     CSLAM_CUDA(cudaMemcpyAsync(poses.data(), D.pose, nKF * sizeof(Pose), cudaMemcpyDeviceToHost, o->stream));
@@ -916,42 +1070,6 @@ extern "C" int cslam_local_ba(cslam_optimizer* o, cslam_ba_problem* p, const vol
         if (r->outlier) for (int s = 0; s < nE; s++) r->outlier[H.perm[s]] = flags[s];
         r->iterations = H.iterations; r->trials = H.trials;
     }
-    free_pool(o);
-    return CSLAM_OK;
-}
-
-extern "C" int cslam_pose_optimization(cslam_optimizer* o, int nframes, const int32_t* offset, float* Tcw, const float* Xw, const float* kp_xy, const float* inv_sigma2,
-                                       int face_w, int face_h, uint8_t* outlier, int32_t* inliers, double* pose_fp64) {
-    if (!o || nframes <= 0 || !offset || !Tcw || !inliers) { set_error("cslam_pose_optimization: bad argument"); return CSLAM_E_BADARG; }
-    if (face_w != face_h || face_w <= 0) { set_error("cube faces must be square"); return CSLAM_E_BADARG; }
-    CSLAM_CUDA(cudaSetDevice(o->device));
-    free_pool(o);
-    const int n = offset[nframes];
-    PoseOptArgs A; std::memset(&A, 0, sizeof(A));
-    int* d_off; float *d_T, *d_X, *d_kp, *d_w; uint8_t *d_out, *d_lvl; int32_t* d_inl; double *d_p64, *d_err;
-    int rc;
-    if ((rc = dalloc(o, &d_off, nframes + 1)) || (rc = dalloc(o, &d_T, (size_t)nframes * 16)) || (rc = dalloc(o, &d_X, (size_t)n * 3)) || (rc = dalloc(o, &d_kp, (size_t)n * 2)) ||
-        (rc = dalloc(o, &d_w, n)) || (rc = dalloc(o, &d_out, n)) || (rc = dalloc(o, &d_lvl, n)) || (rc = dalloc(o, &d_inl, nframes)) || (rc = dalloc(o, &d_p64, (size_t)nframes * 7)) ||
-        (rc = dalloc(o, &d_err, (size_t)n * 2))) return rc;
-    CSLAM_CUDA(cudaMemcpyAsync(d_off, offset, (nframes + 1) * 4, cudaMemcpyHostToDevice, o->stream));
-    CSLAM_CUDA(cudaMemcpyAsync(d_T, Tcw, (size_t)nframes * 64, cudaMemcpyHostToDevice, o->stream));
-    if (n) {
-        CSLAM_CUDA(cudaMemcpyAsync(d_X, Xw, (size_t)n * 12, cudaMemcpyHostToDevice, o->stream));
-        CSLAM_CUDA(cudaMemcpyAsync(d_kp, kp_xy, (size_t)n * 8, cudaMemcpyHostToDevice, o->stream));
-        CSLAM_CUDA(cudaMemcpyAsync(d_w, inv_sigma2, (size_t)n * 4, cudaMemcpyHostToDevice, o->stream));
-    }
-    A.offset = d_off; A.Tcw = d_T; A.Xw = d_X; A.kpxy = d_kp; A.invSigma2 = d_w; A.faceW = face_w; A.faceH = face_h; A.outlier = d_out; A.inliers = d_inl;
-    A.pose64 = d_p64; A.err = d_err; A.level = d_lvl;
-    k_pose_opt<<<nframes, 256, 0, o->stream>>>(A); o->launches++;
-    CSLAM_CUDA(cudaGetLastError());
-    // frames with < 3 correspondences are returned untouched (src/Optimizer.cpp:133-134): copy back only the others
-    std::vector<float> Tout((size_t)nframes * 16);
-    CSLAM_CUDA(cudaMemcpyAsync(Tout.data(), d_T, Tout.size() * 4, cudaMemcpyDeviceToHost, o->stream));
-    if (n && outlier) CSLAM_CUDA(cudaMemcpyAsync(outlier, d_out, n, cudaMemcpyDeviceToHost, o->stream));
-    CSLAM_CUDA(cudaMemcpyAsync(inliers, d_inl, nframes * 4, cudaMemcpyDeviceToHost, o->stream));
-    if (pose_fp64) CSLAM_CUDA(cudaMemcpyAsync(pose_fp64, d_p64, (size_t)nframes * 56, cudaMemcpyDeviceToHost, o->stream));
-    CSLAM_CUDA(cudaStreamSynchronize(o->stream));
-    for (int f = 0; f < nframes; f++) if (offset[f + 1] - offset[f] >= 3) std::memcpy(Tcw + 16 * f, Tout.data() + 16 * f, 64);
     free_pool(o);
     return CSLAM_OK;
 }

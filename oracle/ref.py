@@ -33,6 +33,7 @@ def lib(variant="libref.so"):
             build()
         L = C.CDLL(path)
         L.ref_orb_create.restype = C.c_void_p
+        L.ref_frame_from_image.restype = C.c_void_p
         L.ref_warp_extract_batch.restype = C.c_long
         L.ref_cos_fov_th.restype = C.c_float
         L.ref_arena_used.restype = C.c_size_t
@@ -115,3 +116,36 @@ class RefORBextractor:
         out = np.zeros((h.value, w.value), np.uint8)
         self.ref.L.ref_orb_level_image(self._h, level, _p(out))
         return out
+
+
+class RefFrame:
+    """The reference's Frame built from an image like Tracking does (extraction, ComputeKeyPointRays, AssignFeaturesToGrid)."""
+    GRID = (5, 50, 50)
+
+    def __init__(self, rex, image, mask):
+        image = _u8(image); mask = _u8(mask)
+        self.ref = rex.ref; self.rex = rex
+        self.ref._pinned()
+        self._h = C.c_void_p(self.ref.L.ref_frame_from_image(rex._h, _p(image), _p(mask), image.shape[0], image.shape[1]))
+        self.ref.L.ref_set_pins(0)
+        self.N = self.ref.L.ref_frame_n(self._h)
+        n = self.N
+        self.kps = np.empty(n, KP_DTYPE); self.desc = np.empty((n, 32), np.uint8); self.rays = np.empty((n, 3), np.float32)
+        self.grid_count = np.empty(self.GRID, np.int32)
+        self.ref.L.ref_frame_get(self._h, _p(self.kps), _p(self.desc), _p(self.rays), _p(self.grid_count))
+
+    def __del__(self):
+        try:
+            self.ref.L.ref_frame_destroy(self._h)
+        except Exception:
+            pass
+
+    def grid_cell(self, face, col, row):
+        buf = np.empty(4096, np.int32)
+        n = self.ref.L.ref_frame_grid_cell(self._h, int(face), int(col), int(row), _p(buf), 4096)
+        return buf[:n].copy()
+
+    def features_in_area(self, x, y, r, min_level=-1, max_level=-1):
+        buf = np.empty(8192, np.int32)
+        n = self.ref.L.ref_frame_features_in_area(self._h, C.c_float(x), C.c_float(y), C.c_float(r), int(min_level), int(max_level), _p(buf), 8192)
+        return buf[:n].copy()

@@ -195,6 +195,42 @@ long ref_warp_extract_batch(const uint8_t* fisheyes, int nframes, const float* m
     return s;
 }
 
+// ---- Frame (src/Frame.cpp:104-156): extraction + ComputeKeyPointRays (:746-760) + AssignFeaturesToGrid (:158-176), exactly as Tracking builds it
+struct RefFrame { Frame* F; };
+void* ref_frame_from_image(void* orb, const uint8_t* img, const uint8_t* mask, int rows, int cols) {
+    RefOrb* h = (RefOrb*)orb;
+    cv::Mat im(rows, cols, CV_8UC1, (void*)img), mk(rows, cols, CV_8UC1, (void*)mask);
+    Frame::mbInitialComputations = true;   // grid geometry follows this image size (src/Frame.cpp:141-152)
+    RefFrame* f = new RefFrame; f->F = new Frame(im, mk, 0.0, h->ex, static_cast<ORBVocabulary*>(NULL));
+    return f;
+}
+void ref_frame_destroy(void* fv) { RefFrame* f = (RefFrame*)fv; delete f->F; delete f; }
+int ref_frame_n(void* fv) { return ((RefFrame*)fv)->F->N; }
+void ref_frame_get(void* fv, cv::KeyPoint* kps, uint8_t* desc, float* rays, int32_t* gridCount) {
+    Frame* F = ((RefFrame*)fv)->F;
+    const int n = F->N;
+    if (n && kps) std::memcpy((void*)kps, F->mvKeys.data(), (size_t)n * sizeof(cv::KeyPoint));
+    for (int i = 0; i < n; i++) {
+        if (desc) std::memcpy(desc + 32 * (size_t)i, F->mDescriptors.ptr<uchar>(i), 32);
+        if (rays) for (int c = 0; c < 3; c++) rays[3 * i + c] = F->mvKeyRays[i](c);
+    }
+    if (gridCount)
+        for (int f = 0; f < CUBEMAP_FACES; f++) for (int x = 0; x < CUBEFACE_GRID_COLS; x++) for (int y = 0; y < CUBEFACE_GRID_ROWS; y++)
+            gridCount[(f * CUBEFACE_GRID_COLS + x) * CUBEFACE_GRID_ROWS + y] = (int)F->mGrid[f][x][y].size();
+}
+// grid cell contents in the reference's order: mGrid[face][col][row] (include/Frame.h:129)
+int ref_frame_grid_cell(void* fv, int face, int col, int row, int32_t* idx, int cap) {
+    const std::vector<size_t>& v = ((RefFrame*)fv)->F->mGrid[face][col][row];
+    for (size_t i = 0; i < v.size() && (int)i < cap; i++) idx[i] = (int32_t)v[i];
+    return (int)v.size();
+}
+// Frame::GetFeaturesInArea (src/Frame.cpp:251-716)
+int ref_frame_features_in_area(void* fv, float x, float y, float r, int minLevel, int maxLevel, int32_t* idx, int cap) {
+    const std::vector<size_t> v = ((RefFrame*)fv)->F->GetFeaturesInArea(x, y, r, minLevel, maxLevel);
+    for (size_t i = 0; i < v.size() && (int)i < cap; i++) idx[i] = (int32_t)v[i];
+    return (int)v.size();
+}
+
 // ORBMatcher::DescriptorDistance, src/ORBMatcher.cpp:951-967
 int ref_descriptor_distance(const uint8_t* a, const uint8_t* b) {
     cv::Mat ma(1, 32, CV_8UC1, (void*)a), mb(1, 32, CV_8UC1, (void*)b);

@@ -1,0 +1,103 @@
+"""The drop-in boundary, linked and run on the GPU: dropin/*.cpp (definitions of the reference's ORBextractor / ORBMatcher / Optimizer
+methods on libcubemap_b200.so) compiled against the reference's own unmodified headers and linked with the reference's own Frame / KeyFrame /
+MapPoint / Map classes (oracle/_ref/libdropin.so, recipe oracle/Makefile, harness oracle/dropin_api.cpp). The reference call sites
+Frame::Frame -> (*mpORBextractor)(...), ORBMatcher::SearchByBoW(pKF, F, ...), Optimizer::PoseOptimization(&F),
+Optimizer::LocalBundleAdjustment(pKF, &stop, pMap) run unchanged; results are compared with the oracle / the reference's CPU bodies."""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+from cubemapslam_b200 import config, synth
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+LIB = os.path.join(ROOT, "oracle", "_ref", "libdropin.so")
+KP = np.dtype([("x", "<f4"), ("y", "<f4"), ("size", "<f4"), ("angle", "<f4"), ("response", "<f4"), ("octave", "<i4"), ("class_id", "<i4")])
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+@pytest.fixture(scope="module")
+def dropin(oracle):
+    if not os.path.exists(LIB):
+        pytest.skip("oracle/_ref/libdropin.so is built in the build container (needs the reference tree)")
+    L = C.CDLL(LIB)
+    cfg = config.lafida_450()
+    cp = oracle.cam_params(cfg)
+    L.dropin_set_camera(C.byref(cp))
+    return L, cfg, cp
+
+
+def test_frame_constructor_runs_gpu_extractor(oracle, dropin):
+    """Frame::Frame(im, mask, ts, extractor, voc) of the reference with the drop-in ORBextractor: keypoints / descriptors equal the oracle,
+    and the reference's own ComputeKeyPointRays / AssignFeaturesToGrid ran on them."""
+    L, cfg, cp = dropin
+    mask = config.load_mask("gray_lafida_cubemap_mask_450")
+    m1, m2 = oracle.build_maps(cp)
+    for fi in (0, 3):
+        canvas = oracle.warp(cp, synth.fisheye_frame(cfg, fi), m1, m2)
+        cap = 2100
+        kps = np.zeros(cap, KP); desc = np.zeros((cap, 32), np.uint8); rays = np.zeros((cap, 3), np.float32); grid = np.zeros((5, 50, 50), np.int32)
+        n = L.dropin_frame_from_image(_p(canvas), _p(mask), 1350, 1350, 2000, C.c_float(1.2), 8, 20, 7, cap, _p(kps), _p(desc), _p(rays), _p(grid))
+        rk, rd = oracle.ORBextractor(2000, 1.2, 8, 20, 7, 450, 450)(canvas, mask)
+        assert n == len(rk) > 1000
+        assert np.array_equal(kps[:n].view(np.uint8), rk.view(np.uint8)) and np.array_equal(desc[:n], rd)
+        assert grid.sum() == n and np.allclose(np.linalg.norm(rays[:n], axis=1), 1.0, atol=1e-6)
+
+
+def test_search_by_bow_on_reference_objects(dropin):
+    """ORBMatcher(0.7, true).SearchByBoW(pKF, F, matches) through the reference's KeyFrame / Frame / MapPoint objects: the GPU drop-in and the
+    reference's own CPU body (src/ORBMatcher.cpp:409-539, same objects) must agree exactly."""
+    L, cfg, cp = dropin
+    for seed, n in ((0, 1500), (1, 700)):
+        A, aA, B, aB, perm = synth.descriptor_pair(seed, n=n)
+        rng = np.random.default_rng(40 + seed)
+        nodeA = rng.integers(0, 60, n).astype(np.int32); nodeB = nodeA[perm].copy()
+        nodeB[rng.random(n) < 0.1] = 61
+        valid = (rng.random(n) < 0.8).astype(np.uint8)
+        kA = np.zeros(n, KP); kB = np.zeros(n, KP)
+        kA["x"] = 600; kA["y"] = 600; kB["x"] = 600; kB["y"] = 600; kA["angle"] = aA; kB["angle"] = aB
+        mg = np.zeros(n, np.int32); mc = np.zeros(n, np.int32); ng = C.c_int32(); nc = C.c_int32()
+        L.dropin_search_by_bow(n, _p(kA), _p(A), _p(valid), _p(nodeA), n, _p(kB), _p(B), _p(nodeB), C.c_float(0.7), 1, _p(mg), C.byref(ng), _p(mc), C.byref(nc))
+        assert ng.value == nc.value > 50
+        assert np.array_equal(mg, mc)
+
+
+def test_pose_optimization_on_reference_frame(oracle, dropin):
+    L, cfg, cp = dropin
+    for seed in (5, 6):
+        q = synth.pose_problem(n=300, faceW=450, seed=seed, outlier_frac=0.15)
+        n = len(q["Xw"])
+        octave = np.zeros(n, np.int32)
+        T = np.ascontiguousarray(q["Tcw"], np.float32).copy(); out = np.zeros(n, np.uint8)
+        w = np.ones(n, np.float32)
+        inl = L.dropin_pose_optimization(n, _p(np.ascontiguousarray(q["kpxy"], np.float32)), _p(octave), _p(np.ascontiguousarray(q["Xw"], np.float32)), _p(T), _p(out))
+        r = oracle.pose_opt(q["Tcw"], q["Xw"], q["kpxy"], w, 450, 450)
+        assert inl == r["inliers"] and np.array_equal(out, r["outlier"])
+        assert np.allclose(T.reshape(4, 4), r["Tcw"], atol=2e-6)
+
+
+def test_local_bundle_adjustment_on_reference_map(oracle, dropin):
+    """Optimizer::LocalBundleAdjustment(pKF, &stop, pMap) on a Map built with the reference's KeyFrame / MapPoint / Map API; every key frame is
+    covisible with the current one (every point is seen by all 6), so the local window is the whole problem and equals the oracle's input."""
+    L, cfg, cp = dropin
+    p = synth.ba_problem(nKF=6, nMP=400, kmin=6, kmax=6, faceW=450, seed=21, radius=1.5)
+    nKF, nMP, nE = 6, 400, len(p["eMP"])
+    rng = np.random.default_rng(2)
+    octave = rng.integers(0, 8, nE).astype(np.int32)
+    sc = np.float32(1.0); tab = []
+    for i in range(8):
+        tab.append(np.float32(1.0) / (sc * sc)); sc = sc * np.float32(1.2)
+    inv_sigma2 = np.array([tab[o] for o in octave], np.float32)
+    T = np.ascontiguousarray(p["Tcw"], np.float32).reshape(nKF, 16).copy(); pts = np.ascontiguousarray(p["pts"], np.float32).copy()
+    erased = np.zeros(nE, np.uint8)
+    window = L.dropin_local_ba(nKF, nMP, nE, _p(T), _p(pts), _p(p["eMP"]), _p(p["eKF"]), _p(np.ascontiguousarray(p["kpxy"], np.float32)), _p(octave), 3, _p(erased))
+    assert window == nKF
+    r = oracle.local_ba(p["Tcw"], p["kf_fixed"], p["pts"], p["eMP"], p["eKF"], p["kpxy"], inv_sigma2, 450, 450)
+    assert r["iters"] >= 5
+    assert np.array_equal(erased, r["outlier"])
+    assert np.allclose(T.reshape(nKF, 4, 4), r["Tcw"], atol=2e-6) and np.allclose(pts, r["pts"], atol=2e-6)
