@@ -157,3 +157,74 @@ def pose_problem(n=600, faceW=650, seed=77, outlier_frac=0.1, radius=1.5):
     Xw = p["pts_true"][p["eMP"][idx]].astype(np.float32)
     return dict(Tcw=p["Tcw"][1].copy(), Xw=Xw, kpxy=p["kpxy"][idx].copy(), inv_sigma2=p["inv_sigma2"][idx].copy(), faceW=faceW, faceH=faceW,
                 Tcw_true=p["Tcw_true"][1])
+
+
+# ----------------------------------------------------------------------------- tracking (projection matching) scenario
+def _pixel_to_ray(px, py, W):
+    """Unit bearing vector of a canvas pixel (plain float64 pinhole per face; generator only, the exact reference arithmetic lives in the library)."""
+    f = W / 2.0
+    c, r = int(px // W), int(py // W)
+    face = {(1, 1): 0, (0, 1): 1, (2, 1): 2, (1, 0): 3, (1, 2): 4}.get((c, r))
+    if face is None:
+        return None
+    lx, ly = (px - c * W - f) / f, (py - r * W - f) / f
+    v = {0: (lx, ly, 1.0), 1: (-1.0, ly, lx), 2: (1.0, ly, -lx), 4: (lx, 1.0, -ly), 3: (lx, -1.0, ly)}[face]
+    v = np.array(v)
+    return v / np.linalg.norm(v)
+
+
+def tracking_pair(seed=0, n=2000, faceW=650, motion=0.02, rot=0.01, mp_frac=0.8, extra_frac=0.15):
+    """A (LastFrame, CurrentFrame) pair for ORBMatcher::SearchByProjection: LastFrame key points spread over all five faces with MapPoints at
+    random depth, CurrentFrame = the same points seen after a small motion (+ pixel noise, descriptor bit flips, unrelated extra features).
+    All arrays float32 / uint8 / int32 like the reference's containers. kps use the cv::KeyPoint field order (x, y, size, angle, response, octave, class_id)."""
+    rng = np.random.default_rng(7000 + seed)
+    KP = np.dtype([("x", "<f4"), ("y", "<f4"), ("size", "<f4"), ("angle", "<f4"), ("response", "<f4"), ("octave", "<i4"), ("class_id", "<i4")])
+    W = faceW
+    tiles = [(1, 1), (0, 1), (2, 1), (1, 0), (1, 2)]
+    kL = np.zeros(n, KP); Xw = np.zeros((n, 3), np.float32)
+    TcwL = np.eye(4, dtype=np.float32)
+    Rc = _rodrigues(rng.normal(0, rot, 3)); tc = rng.normal(0, motion, 3)
+    TcwC = np.eye(4, dtype=np.float32); TcwC[:3, :3] = Rc; TcwC[:3, 3] = tc
+    rays = []
+    for i in range(n):
+        c, r = tiles[rng.integers(0, 5)]
+        # a third of the points hug the face borders so that search windows cross face seams
+        u, v = rng.uniform(1, W - 1, 2)
+        if i % 3 == 0:
+            u = rng.choice([rng.uniform(0.5, 25), rng.uniform(W - 25, W - 0.5)])
+        if i % 6 == 0:
+            v = rng.choice([rng.uniform(0.5, 25), rng.uniform(W - 25, W - 0.5)])
+        kL["x"][i] = c * W + u; kL["y"][i] = r * W + v
+        ray = _pixel_to_ray(float(kL["x"][i]), float(kL["y"][i]), W)
+        rays.append(ray)
+        Xw[i] = (ray * rng.uniform(2.0, 12.0)).astype(np.float32)
+    kL["octave"] = rng.integers(0, 8, n); kL["angle"] = rng.uniform(0, 360, n).astype(np.float32); kL["size"] = 31; kL["class_id"] = -1
+    dL = rng.integers(0, 256, (n, 32), dtype=np.uint8)
+    hasMP = (rng.random(n) < mp_frac).astype(np.uint8)
+    # current frame: project, perturb
+    kC = []; dC = []; src = []
+    for i in range(n):
+        Xc = Rc @ Xw[i].astype(np.float64) + tc
+        uv = _rays_to_cubemap(Xc[0], Xc[1], Xc[2], W)
+        if uv is None or rng.random() < 0.1:
+            continue
+        x, y = uv[0] + rng.normal(0, 1.5), uv[1] + rng.normal(0, 1.5)
+        if _pixel_to_ray(x, y, W) is None:
+            continue
+        d = dL[i] ^ np.packbits(rng.random(256) < 0.06, bitorder="little")
+        oct_ = int(np.clip(kL["octave"][i] + rng.integers(-1, 2), 0, 7))
+        kC.append((x, y, 31, float((kL["angle"][i] + rng.uniform(-5, 5)) % 360), 0, oct_, -1)); dC.append(d); src.append(i)
+    for _ in range(int(extra_frac * n)):
+        c, r = tiles[rng.integers(0, 5)]
+        kC.append((c * W + rng.uniform(0.5, W - 0.5), r * W + rng.uniform(0.5, W - 0.5), 31, float(rng.uniform(0, 360)), 0, int(rng.integers(0, 8)), -1))
+        dC.append(rng.integers(0, 256, 32, dtype=np.uint8)); src.append(-1)
+    perm = rng.permutation(len(kC))
+    kC = np.array([kC[j] for j in perm], KP); dC = np.stack([dC[j] for j in perm]); src = np.array([src[j] for j in perm], np.int32)
+    order = np.lexsort((kC["x"], kC["y"], kC["octave"]))          # extractor order: level-major
+    kC, dC, src = kC[order], dC[order], src[order]
+    scale = np.ones(8, np.float32)
+    for l in range(1, 8):
+        scale[l] = scale[l - 1] * np.float32(1.2)
+    mpObs = (rng.random(n) < 0.9).astype(np.int32)
+    curTaken = (rng.random(len(kC)) < 0.03).astype(np.uint8)
+    return dict(kLast=kL, dLast=dL, TcwLast=TcwL, hasMP=hasMP, Xw=Xw, mpObs=mpObs, kCur=kC, dCur=dC, TcwCur=TcwC, src=src, scale=scale, curTaken=curTaken, faceW=W)

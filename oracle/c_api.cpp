@@ -6,6 +6,7 @@
 #include "ba.h"
 #include "cam_model.h"
 #include "cvprim.h"
+#include "frame_index.h"
 #include "orb_extractor.h"
 #include "orb_matcher.h"
 
@@ -114,6 +115,44 @@ void orc_match_bruteforce_batch(const uint8_t* descA, const float* angA, int nA,
     for (int t = 1; t < nthreads; t++) th.emplace_back(work, t);
     work(0);
     for (auto& x : th) x.join();
+}
+
+// ---- per-frame indexing (rays, 5x50x50 grid) and windowed lookup
+void orc_key_point_rays(const KeyPoint* kps, int n, int faceW, int faceH, float* rays, int* faces) {
+    for (int i = 0; i < n; i++) { const int f = fi_pixel_to_ray(kps[i].x, kps[i].y, faceW, faceH, rays + 3 * i); if (faces) faces[i] = f; }
+}
+struct GridHandle { FrameGrid g; std::vector<KeyPoint> kps; };
+void* orc_grid_create(const KeyPoint* kps, int n, int faceW, int faceH) {
+    GridHandle* h = new GridHandle; h->kps.assign(kps, kps + n); h->g.build(h->kps.data(), n, faceW, faceH); return h;
+}
+void orc_grid_destroy(void* h) { delete (GridHandle*)h; }
+// CSR view: cellStart[5*50*50+1], cellIdx[n] (cells in (face, col, row) order, indices ascending inside a cell)
+int orc_grid_csr(void* hv, int* cellStart, int* cellIdx) {
+    GridHandle* h = (GridHandle*)hv; int pos = 0;
+    for (size_t c = 0; c < h->g.cells.size(); c++) { cellStart[c] = pos; for (int i : h->g.cells[c]) cellIdx[pos++] = i; }
+    cellStart[h->g.cells.size()] = pos;
+    return pos;
+}
+int orc_features_in_area(void* hv, float x, float y, float r, int minLevel, int maxLevel, int* out, int cap) {
+    GridHandle* h = (GridHandle*)hv; std::vector<int> v;
+    fi_features_in_area(h->g, h->kps.data(), x, y, r, minLevel, maxLevel, v);
+    for (size_t i = 0; i < v.size() && (int)i < cap; i++) out[i] = v[i];
+    return (int)v.size();
+}
+
+int orc_search_by_projection_last(void* hv, const uint8_t* dCur, const float* TcwCur, const float* scaleFactors, const KeyPoint* kLast, int nLast, const uint8_t* hasMP,
+                                  const float* Xw, const uint8_t* dMP, const int* mpObs, const uint8_t* curTaken, float cosFovTh, float th, int checkOri, int* matchCur) {
+    GridHandle* h = (GridHandle*)hv;
+    return fi_search_by_projection_last(h->g, h->kps.data(), dCur, (int)h->kps.size(), TcwCur, scaleFactors, kLast, nLast, hasMP, Xw, dMP, mpObs, curTaken, cosFovTh, th,
+                                        checkOri != 0, matchCur);
+}
+int orc_search_by_projection_local(void* hv, const uint8_t* dF, const float* scaleFactors, int nMP, const uint8_t* inView, const float* projXY, const int* level,
+                                   const float* viewCos, const uint8_t* dMP, const int* mpObs, const uint8_t* fTaken, float th, float nnratio, int* matchF) {
+    GridHandle* h = (GridHandle*)hv;
+    return fi_search_by_projection_local(h->g, h->kps.data(), dF, (int)h->kps.size(), scaleFactors, nMP, inView, projXY, level, viewCos, dMP, mpObs, fTaken, th, nnratio, matchF);
+}
+void orc_ray_to_cubemap(const float* xyz, int n, int faceW, int faceH, float* uv, int* faces) {
+    for (int i = 0; i < n; i++) faces[i] = fi_ray_to_cubemap(xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2], faceW, faceH, uv[2 * i], uv[2 * i + 1]);
 }
 
 // ---- bundle adjustment

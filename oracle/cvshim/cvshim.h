@@ -125,6 +125,7 @@ struct KeyPoint {
 };
 
 class _OutputArray;
+struct MatScaleExpr;
 // Mat::zeros / ones / eye return an initializer EXPRESSION in OpenCV: assigning it to an existing Mat of the same size and type fills
 // that Mat in place (m.create() is a no-op, then m = Scalar), which ORBextractor's computeDescriptors relies on for its row-range view.
 struct MatInit { int rows, cols, type, kind; };
@@ -206,7 +207,7 @@ public:
     static MatInit zeros(Size s, int type) { return MatInit{s.height, s.width, type, 0}; }
     static MatInit ones(int r, int c, int type) { return MatInit{r, c, type, 1}; }
     static MatInit eye(int r, int c, int type) { return MatInit{r, c, type, 2}; }
-    Mat t() const { Mat m(cols, rows, flags); for (int r = 0; r < rows; r++) for (int c = 0; c < cols; c++) m.set(c, r, get(r, c)); return m; }
+    struct MatScaleExpr t() const;   // lazy, like cv::MatExpr
     // cv::Mat::dot: element products accumulated in double (dotProd_<float> returns double)
     double dot(const Mat& o) const {
         assert(total() == o.total());
@@ -221,18 +222,32 @@ private:
 
 template <class T, int n> Vec<T, n>::Vec(const Mat& m) { assert((int)m.total() == n); for (int i = 0; i < n; i++) val[i] = (T)(m.rows == 1 ? m.get(0, i) : m.get(i, 0)); }
 
-// ---- matrix arithmetic. OpenCV evaluates `A*B+C` as ONE gemm: D = alpha*A*B + beta*C with the inner product and the
-// final alpha/beta combination in double for CV_32F (GEMMSingleMul<float,double>), rounded once to the element type.
-// MatMulExpr keeps the product unevaluated so that `R*x+t` / `R*x-t` reproduce that single rounding.
+// ---- matrix arithmetic. OpenCV evaluates `A*B+C` as ONE gemm, D = alpha*op(A)*op(B) + beta*C, and cv::Mat::t() / unary minus / scalar
+// factors stay lazy (MatExpr), so `-R.t()*t` is a single gemm with GEMM_1_T and alpha = -1. Pinned against cv2.gemm 4.13
+// (tests/test_oracle_cv2.py::test_gemm_models):
+//   * flags == 0, CV_32F, 2 <= len <= 4 and len == D.cols or D.rows (the "small matrix" path: R*x+t, R*R): the inner product is accumulated in
+//     FLOAT, left to right, without FMA, then D = (float)((double)t*alpha + (double)c*beta);
+//   * everything else (any transposed operand, larger sizes, CV_64F): inner product accumulated in double.
 struct MatMulExpr {
-    Mat a, b; double alpha;
+    Mat a, b; double alpha; bool ta, tb;
     Mat eval(const Mat* c = nullptr, double beta = 0) const {
-        assert(a.cols == b.rows && a.type() == b.type());
-        Mat d(a.rows, b.cols, a.type());
-        for (int i = 0; i < a.rows; i++) for (int j = 0; j < b.cols; j++) {
-            double s = 0;
-            for (int k = 0; k < a.cols; k++) s += a.get(i, k) * b.get(k, j);
-            double v = s * alpha;
+        const int ar = ta ? a.cols : a.rows, ac = ta ? a.rows : a.cols, br = tb ? b.cols : b.rows, bc = tb ? b.rows : b.cols;
+        assert(ac == br && a.type() == b.type());
+        (void)br;
+        Mat d(ar, bc, a.type());
+        const int len = ac;
+        const bool smallF = !ta && !tb && a.type() == CV_32F && len >= 2 && len <= 4 && (len == bc || len == ar);
+        for (int i = 0; i < ar; i++) for (int j = 0; j < bc; j++) {
+            double v;
+            if (smallF) {
+                float t = a.at<float>(i, 0) * b.at<float>(0, j);
+                for (int k = 1; k < len; k++) t = t + a.at<float>(i, k) * b.at<float>(k, j);
+                v = (double)t * alpha;
+            } else {
+                double sacc = 0;
+                for (int k = 0; k < len; k++) sacc += (ta ? a.get(k, i) : a.get(i, k)) * (tb ? b.get(j, k) : b.get(k, j));
+                v = sacc * alpha;
+            }
             if (c) v += c->get(i, j) * beta;
             d.set(i, j, v);
         }
@@ -240,11 +255,31 @@ struct MatMulExpr {
     }
     operator Mat() const { return eval(); }
 };
-static inline MatMulExpr operator*(const Mat& a, const Mat& b) { return MatMulExpr{a, b, 1.0}; }
-static inline MatMulExpr operator*(const MatMulExpr& e, const Mat& b) { return MatMulExpr{e.eval(), b, 1.0}; }
+// alpha * A or alpha * A^T, unevaluated
+struct MatScaleExpr {
+    Mat a; double alpha; bool t;
+    operator Mat() const {
+        Mat d(t ? a.cols : a.rows, t ? a.rows : a.cols, a.type());
+        for (int i = 0; i < d.rows; i++) for (int j = 0; j < d.cols; j++) { const double v = t ? a.get(j, i) : a.get(i, j); d.set(i, j, alpha == 1.0 ? v : v * alpha); }
+        return d;
+    }
+    MatScaleExpr t_() const { return MatScaleExpr{a, alpha, !t}; }
+};
+inline MatScaleExpr Mat::t() const { return MatScaleExpr{*this, 1.0, true}; }
+static inline MatMulExpr operator*(const Mat& a, const Mat& b) { return MatMulExpr{a, b, 1.0, false, false}; }
+static inline MatMulExpr operator*(const MatScaleExpr& s, const Mat& b) { return MatMulExpr{s.a, b, s.alpha, s.t, false}; }
+static inline MatMulExpr operator*(const Mat& a, const MatScaleExpr& s) { return MatMulExpr{a, s.a, s.alpha, false, s.t}; }
+static inline MatMulExpr operator*(const MatMulExpr& e, const Mat& b) { return MatMulExpr{e.eval(), b, 1.0, false, false}; }
 static inline Mat operator+(const MatMulExpr& e, const Mat& c) { return e.eval(&c, 1.0); }
 static inline Mat operator-(const MatMulExpr& e, const Mat& c) { return e.eval(&c, -1.0); }
-static inline MatMulExpr operator-(const MatMulExpr& e) { return MatMulExpr{e.a, e.b, -e.alpha}; }
+static inline Mat operator+(const Mat& c, const MatMulExpr& e) { return e.eval(&c, 1.0); }
+static inline MatMulExpr operator-(const MatMulExpr& e) { return MatMulExpr{e.a, e.b, -e.alpha, e.ta, e.tb}; }
+static inline MatScaleExpr operator-(const Mat& a) { return MatScaleExpr{a, -1.0, false}; }
+static inline MatScaleExpr operator-(const MatScaleExpr& s) { return MatScaleExpr{s.a, -s.alpha, s.t}; }
+static inline MatScaleExpr operator*(double k, const Mat& a) { return MatScaleExpr{a, k, false}; }
+static inline MatScaleExpr operator*(const Mat& a, double k) { return MatScaleExpr{a, k, false}; }
+static inline MatScaleExpr operator*(double k, const MatScaleExpr& s) { return MatScaleExpr{s.a, k * s.alpha, s.t}; }
+static inline MatScaleExpr operator/(const Mat& a, double k) { return MatScaleExpr{a, 1.0 / k, false}; }
 static inline Mat binop(const Mat& a, const Mat& b, int sign) {
     assert(a.rows == b.rows && a.cols == b.cols);
     Mat d(a.rows, a.cols, a.type());
@@ -256,21 +291,8 @@ static inline Mat binop(const Mat& a, const Mat& b, int sign) {
 }
 static inline Mat operator+(const Mat& a, const Mat& b) { return binop(a, b, 1); }
 static inline Mat operator-(const Mat& a, const Mat& b) { return binop(a, b, -1); }
-// scaled matrix (MatExpr alpha*A): `-A`, `s*A`, `A/s` stay lazy so that `-R.t()*t` is one gemm with alpha = -1
-struct MatScaleExpr {
-    Mat a; double alpha;
-    operator Mat() const { Mat d(a.rows, a.cols, a.type()); for (int i = 0; i < a.rows; i++) for (int j = 0; j < a.cols; j++) d.set(i, j, a.get(i, j) * alpha); return d; }
-    Mat t() const { return Mat(*this).t(); }
-};
-static inline MatScaleExpr operator-(const Mat& a) { return MatScaleExpr{a, -1.0}; }
-static inline MatScaleExpr operator*(double s, const Mat& a) { return MatScaleExpr{a, s}; }
-static inline MatScaleExpr operator*(const Mat& a, double s) { return MatScaleExpr{a, s}; }
-static inline MatScaleExpr operator/(const Mat& a, double s) { return MatScaleExpr{a, 1.0 / s}; }
-static inline MatMulExpr operator*(const MatScaleExpr& s, const Mat& b) { return MatMulExpr{s.a, b, s.alpha}; }
-static inline MatMulExpr operator*(const Mat& a, const MatScaleExpr& s) { return MatMulExpr{a, s.a, s.alpha}; }
 static inline Mat operator+(const MatScaleExpr& s, const Mat& b) { return binop(Mat(s), b, 1); }
 static inline Mat operator-(const MatScaleExpr& s, const Mat& b) { return binop(Mat(s), b, -1); }
-static inline Mat operator+(const Mat& a, const MatMulExpr& e) { return e.eval(&a, 1.0); }
 
 // cv::norm(Mat) NORM_L2: sum of squares in double, sqrt
 static inline double norm(const Mat& m) { double s = 0; for (int i = 0; i < m.rows; i++) for (int j = 0; j < m.cols; j++) { const double v = m.get(i, j); s += v * v; } return std::sqrt(s); }
@@ -302,6 +324,7 @@ public:
     _InputArray(const Mat& m) : m_(const_cast<Mat*>(&m)) {}
     template <class T> _InputArray(const Mat_<T>& m) : m_(const_cast<Mat*>(static_cast<const Mat*>(&m))) {}
     _InputArray(const MatMulExpr& e) : own_(new Mat(e.eval())), m_(own_.get()) {}
+    _InputArray(const MatScaleExpr& e) : own_(new Mat(e)), m_(own_.get()) {}
     _InputArray(const MatInit& e) : own_(new Mat(e)), m_(own_.get()) {}
     Mat getMat() const { return m_ ? *m_ : Mat(); }
     bool empty() const { return !m_ || m_->empty(); }

@@ -219,6 +219,66 @@ def match_bruteforce_batch(descA, angA, descB, angB, nnratio=0.6, thLow=50, chec
     return nm, m
 
 
+# ----------------------------------------------------------------------------- per-frame indexing
+def key_point_rays(kps, faceW, faceH):
+    kps = np.ascontiguousarray(kps); n = len(kps)
+    rays = np.zeros((n, 3), np.float32); faces = np.zeros(n, np.int32)
+    lib().orc_key_point_rays(_p(kps), n, int(faceW), int(faceH), _p(rays), _p(faces))
+    return rays, faces
+
+
+class FrameGrid:
+    """Frame::AssignFeaturesToGrid + GetFeaturesInArea (reference src/Frame.cpp:158-176,251-716)."""
+    NCELLS = 5 * 50 * 50
+
+    def __init__(self, kps, faceW, faceH):
+        self.kps = np.ascontiguousarray(kps); self.n = len(self.kps)
+        lib().orc_grid_create.restype = C.c_void_p
+        self._h = C.c_void_p(lib().orc_grid_create(_p(self.kps), self.n, int(faceW), int(faceH)))
+
+    def __del__(self):
+        try:
+            lib().orc_grid_destroy(self._h)
+        except Exception:
+            pass
+
+    def csr(self):
+        start = np.zeros(self.NCELLS + 1, np.int32); idx = np.zeros(max(self.n, 1), np.int32)
+        m = lib().orc_grid_csr(self._h, _p(start), _p(idx))
+        return start, idx[:m]
+
+    def features_in_area(self, x, y, r, min_level=-1, max_level=-1):
+        buf = np.empty(8192, np.int32)
+        n = lib().orc_features_in_area(self._h, C.c_float(x), C.c_float(y), C.c_float(r), int(min_level), int(max_level), _p(buf), 8192)
+        return buf[:n].copy()
+
+
+    def search_by_projection_last(self, dCur, TcwCur, scale_factors, kLast, hasMP, Xw, dMP, mpObs, curTaken, cosFovTh, th, checkOri=True):
+        """ORBMatcher::SearchByProjection(CurrentFrame, LastFrame, th, mono) (reference src/ORBMatcher.cpp:130-251); self = CurrentFrame's grid."""
+        dCur = _u8(dCur); TcwCur = _f32(TcwCur).reshape(16); sf = _f32(scale_factors); kLast = np.ascontiguousarray(kLast)
+        hasMP = _u8(hasMP); Xw = _f32(Xw); dMP = _u8(dMP); mpObs = _i32(mpObs); curTaken = _u8(curTaken)
+        match = np.empty(self.n, np.int32)
+        n = lib().orc_search_by_projection_last(self._h, _p(dCur), _p(TcwCur), _p(sf), _p(kLast), len(kLast), _p(hasMP), _p(Xw), _p(dMP), _p(mpObs), _p(curTaken),
+                                                C.c_float(cosFovTh), C.c_float(th), int(checkOri), _p(match))
+        return n, match
+
+    def search_by_projection_local(self, dF, scale_factors, inView, projXY, level, viewCos, dMP, mpObs, fTaken, th, nnratio):
+        """ORBMatcher::SearchByProjection(F, vpMapPoints, th) (reference src/ORBMatcher.cpp:51-128); self = F's grid."""
+        dF = _u8(dF); sf = _f32(scale_factors); inView = _u8(inView); projXY = _f32(projXY); level = _i32(level); viewCos = _f32(viewCos)
+        dMP = _u8(dMP); mpObs = _i32(mpObs); fTaken = _u8(fTaken)
+        match = np.empty(self.n, np.int32)
+        n = lib().orc_search_by_projection_local(self._h, _p(dF), _p(sf), len(inView), _p(inView), _p(projXY), _p(level), _p(viewCos), _p(dMP), _p(mpObs), _p(fTaken),
+                                                 C.c_float(th), C.c_float(nnratio), _p(match))
+        return n, match
+
+
+def ray_to_cubemap(xyz, faceW, faceH):
+    xyz = _f32(xyz).reshape(-1, 3); n = len(xyz)
+    uv = np.zeros((n, 2), np.float32); faces = np.zeros(n, np.int32)
+    lib().orc_ray_to_cubemap(_p(xyz), n, int(faceW), int(faceH), _p(uv), _p(faces))
+    return uv, faces
+
+
 # ----------------------------------------------------------------------------- bundle adjustment
 def local_ba(Tcw, kf_fixed, pts, eMP, eKF, kpxy, inv_sigma2, faceW, faceH, its1=5, its2=10, stop_flag=None):
     Tcw = _f32(Tcw).copy(); pts = _f32(pts).copy()

@@ -83,6 +83,33 @@ class Ref:
         return self.L.ref_warp_extract_batch(_p(fisheyes), fisheyes.shape[0], _p(m1), _p(m2), _p(mask), int(nfeatures), C.c_float(scaleFactor), int(nlevels),
                                              int(iniTh), int(minTh), int(nthreads))
 
+    def search_by_projection_last(self, kCur, dCur, TcwCur, kLast, TcwLast, hasMP, Xw, dMP, mpObs, curTaken, th, checkOri=True):
+        kCur = np.ascontiguousarray(kCur); kLast = np.ascontiguousarray(kLast)
+        a = [_u8(dCur), _f32(TcwCur).reshape(16), _f32(TcwLast).reshape(16), _u8(hasMP), _f32(Xw), _u8(dMP), np.ascontiguousarray(mpObs, np.int32), _u8(curTaken)]
+        match = np.empty(len(kCur), np.int32)
+        self.L.ref_set_camera(C.byref(self.cp))
+        n = self.L.ref_search_by_projection_last(len(kCur), _p(kCur), _p(a[0]), _p(a[1]), len(kLast), _p(kLast), _p(a[2]), _p(a[3]), _p(a[4]), _p(a[5]), _p(a[6]), _p(a[7]),
+                                                 C.c_float(th), int(checkOri), _p(match))
+        return n, match
+
+    def search_by_projection_local(self, kF, dF, inView, projXY, level, viewCos, dMP, mpObs, fTaken, th, nnratio):
+        kF = np.ascontiguousarray(kF)
+        a = [_u8(dF), _u8(inView), _f32(projXY), np.ascontiguousarray(level, np.int32), _f32(viewCos), _u8(dMP), np.ascontiguousarray(mpObs, np.int32), _u8(fTaken)]
+        match = np.empty(len(kF), np.int32)
+        self.L.ref_set_camera(C.byref(self.cp))
+        n = self.L.ref_search_by_projection_local(len(kF), _p(kF), _p(a[0]), len(a[1]), _p(a[1]), _p(a[2]), _p(a[3]), _p(a[4]), _p(a[5]), _p(a[6]), _p(a[7]), C.c_float(th),
+                                                  C.c_float(nnratio), _p(match))
+        return n, match
+
+    def ray_to_cubemap(self, xyz):
+        xyz = _f32(xyz).reshape(-1, 3); uv = np.zeros((len(xyz), 2), np.float32); faces = np.zeros(len(xyz), np.int32)
+        self.L.ref_set_camera(C.byref(self.cp))
+        for i in range(len(xyz)):
+            u = C.c_float(); v = C.c_float()
+            faces[i] = self.L.ref_ray_to_cubemap(C.c_float(xyz[i, 0]), C.c_float(xyz[i, 1]), C.c_float(xyz[i, 2]), C.byref(u), C.byref(v))
+            uv[i] = (u.value, v.value)
+        return uv, faces
+
     def descriptor_distance(self, a, b):
         a = _u8(a); b = _u8(b)
         return self.L.ref_descriptor_distance(_p(a), _p(b))

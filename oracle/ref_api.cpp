@@ -231,6 +231,108 @@ int ref_frame_features_in_area(void* fv, float x, float y, float r, int minLevel
     return (int)v.size();
 }
 
+// ---- projection matchers of the reference on objects built from flat arrays (what Tracking holds after Frame::Frame)
+namespace {
+struct KpPOD { float x, y, size, angle, response; int octave, class_id; };
+cv::Mat mat_from(const float* T, int r, int c) { cv::Mat m(r, c, CV_32F); for (int i = 0; i < r * c; i++) m.at<float>(i / c, i % c) = T[i]; return m; }
+Frame* make_frame(int n, const KpPOD* kps, const uint8_t* desc, const float* Tcw, int nlevels, float scaleFactor) {
+    Frame* F = new Frame();
+    F->mnId = Frame::nNextId++;
+    F->N = n;
+    F->mvKeys.resize(n);
+    if (n) std::memcpy((void*)F->mvKeys.data(), kps, (size_t)n * sizeof(KpPOD));
+    F->mDescriptors = cv::Mat(n, 32, CV_8UC1);
+    for (int i = 0; i < n; i++) std::memcpy(F->mDescriptors.ptr<uchar>(i), desc + 32 * (size_t)i, 32);
+    F->mvKeyRays.resize(n);
+    for (int i = 0; i < n; i++) CamModelGeneral::GetCamera()->TransformCubemapToRays(F->mvKeyRays[i], F->mvKeys[i].pt);   // Frame::ComputeKeyPointRays
+    F->mvpMapPoints.assign(n, static_cast<MapPoint*>(NULL));
+    F->mvbOutlier.assign(n, false);
+    F->mnScaleLevels = nlevels; F->mfScaleFactor = scaleFactor; F->mfLogScaleFactor = log(scaleFactor);
+    F->mvScaleFactors.resize(nlevels); F->mvLevelSigma2.resize(nlevels); F->mvInvScaleFactors.resize(nlevels); F->mvInvLevelSigma2.resize(nlevels);
+    F->mvScaleFactors[0] = 1.0f; F->mvLevelSigma2[0] = 1.0f;
+    for (int i = 1; i < nlevels; i++) { F->mvScaleFactors[i] = F->mvScaleFactors[i - 1] * scaleFactor; F->mvLevelSigma2[i] = F->mvScaleFactors[i] * F->mvScaleFactors[i]; }
+    for (int i = 0; i < nlevels; i++) { F->mvInvScaleFactors[i] = 1.0f / F->mvScaleFactors[i]; F->mvInvLevelSigma2[i] = 1.0f / F->mvLevelSigma2[i]; }
+    if (Tcw) F->SetPose(mat_from(Tcw, 4, 4));
+    // Frame::AssignFeaturesToGrid is private: replay it (src/Frame.cpp:158-176) with the public PosInGrid
+    const int W3 = 3 * CamModelGeneral::GetCamera()->GetCubeFaceWidth();
+    Frame::mnMinX = 0.0f; Frame::mnMaxX = (float)W3; Frame::mnMinY = 0.0f; Frame::mnMaxY = (float)(3 * CamModelGeneral::GetCamera()->GetCubeFaceHeight());
+    Frame::mfGridElementLengthInv = static_cast<float>(3 * CUBEFACE_GRID_COLS) / static_cast<float>(Frame::mnMaxX - Frame::mnMinX);
+    Frame::mfGridElementLength = static_cast<float>(Frame::mnMaxX - Frame::mnMinX) / static_cast<float>(3 * CUBEFACE_GRID_COLS);
+    for (int i = 0; i < n; i++) {
+        CamModelGeneral::eFace face; int gx, gy;
+        if (F->PosInGrid(F->mvKeys[i], face, gx, gy)) F->mGrid[face][gx][gy].push_back(i);
+    }
+    return F;
+}
+}  // namespace
+
+// ORBMatcher(nnratio, checkOri).SearchByProjection(CurrentFrame, LastFrame, th, true)   src/ORBMatcher.cpp:130-251
+// matchCur[i2]: index i of the LastFrame feature whose MapPoint now sits in CurrentFrame.mvpMapPoints[i2], -1 empty, -2 a pre-existing MapPoint.
+int ref_search_by_projection_last(int nCur, const KpPOD* kCur, const uint8_t* dCur, const float* TcwCur, int nLast, const KpPOD* kLast, const float* TcwLast,
+                                  const uint8_t* hasMP, const float* Xw, const uint8_t* dMP, const int32_t* mpObs, const uint8_t* curTaken, float th, int checkOri,
+                                  int32_t* matchCur) {
+    Map map;
+    Frame* cur = make_frame(nCur, kCur, dCur, TcwCur, 8, 1.2f);
+    Frame* last = make_frame(nLast, kLast, dMP, TcwLast, 8, 1.2f);   // its descriptors double as the MapPoints' (MapPoint ctor copies row idxF)
+    KeyFrame* kfObs = new KeyFrame(*last, &map, NULL);
+    std::map<MapPoint*, int> idxOf; std::vector<MapPoint*> owned;
+    for (int i = 0; i < nLast; i++) {
+        if (!hasMP[i]) continue;
+        MapPoint* mp = new MapPoint(mat_from(Xw + 3 * i, 3, 1), &map, last, i);
+        if (mpObs[i] > 0) mp->AddObservation(kfObs, i);
+        last->mvpMapPoints[i] = mp; idxOf[mp] = i; owned.push_back(mp);
+    }
+    const float P0[3] = {0, 0, 1};
+    for (int i2 = 0; i2 < nCur; i2++) if (curTaken[i2]) { MapPoint* mp = new MapPoint(mat_from(P0, 3, 1), kfObs, &map); mp->AddObservation(kfObs, 0); cur->mvpMapPoints[i2] = mp; idxOf[mp] = -2; owned.push_back(mp); }
+    ORBMatcher matcher(0.9f, checkOri != 0);
+    const int n = matcher.SearchByProjection(*cur, *last, th, true);
+    for (int i2 = 0; i2 < nCur; i2++) matchCur[i2] = cur->mvpMapPoints[i2] ? idxOf[cur->mvpMapPoints[i2]] : -1;
+    for (MapPoint* mp : owned) delete mp;
+    delete kfObs; delete cur; delete last;
+    return n;
+}
+
+// ORBMatcher(nnratio).SearchByProjection(F, vpMapPoints, th)   src/ORBMatcher.cpp:51-128 ; the MapPoints carry what Frame::isInFrustum left in them
+int ref_search_by_projection_local(int nF, const KpPOD* kF, const uint8_t* dF, int nMP, const uint8_t* inView, const float* projXY, const int32_t* level, const float* viewCos,
+                                   const uint8_t* dMP, const int32_t* mpObs, const uint8_t* fTaken, float th, float nnratio, int32_t* matchF) {
+    Map map;
+    const float I4[16] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1};
+    Frame* F = make_frame(nF, kF, dF, I4, 8, 1.2f);
+    std::vector<KpPOD> kd(nMP); for (int m = 0; m < nMP; m++) { kd[m] = KpPOD{700, 700, 31, 0, 0, 0, -1}; }
+    Frame* holder = make_frame(nMP, kd.data(), dMP, I4, 8, 1.2f);   // only lends its descriptor rows to the MapPoint constructor
+    KeyFrame* kfObs = new KeyFrame(*holder, &map, NULL);
+    std::map<MapPoint*, int> idxOf; std::vector<MapPoint*> mps(nMP), owned;
+    const float P0[3] = {0, 0, 1};
+    for (int m = 0; m < nMP; m++) {
+        MapPoint* mp = new MapPoint(mat_from(P0, 3, 1), &map, holder, m);
+        if (mpObs[m] > 0) mp->AddObservation(kfObs, m);
+        mp->mbTrackInView = inView[m] != 0; mp->mTrackProjX = projXY[2 * m]; mp->mTrackProjY = projXY[2 * m + 1]; mp->mnTrackScaleLevel = level[m]; mp->mTrackViewCos = viewCos[m];
+        mps[m] = mp; idxOf[mp] = m; owned.push_back(mp);
+    }
+    for (int i = 0; i < nF; i++) if (fTaken[i]) { MapPoint* mp = new MapPoint(mat_from(P0, 3, 1), kfObs, &map); mp->AddObservation(kfObs, 0); F->mvpMapPoints[i] = mp; idxOf[mp] = -2; owned.push_back(mp); }
+    ORBMatcher matcher(nnratio, true);
+    const int n = matcher.SearchByProjection(*F, mps, th);
+    for (int i = 0; i < nF; i++) matchF[i] = F->mvpMapPoints[i] ? idxOf[F->mvpMapPoints[i]] : -1;
+    for (MapPoint* mp : owned) delete mp;
+    delete kfObs; delete F; delete holder;
+    return n;
+}
+// CamModelGeneral::TransformRaysToCubemap(up, vp, x, y, z)
+int ref_ray_to_cubemap(float x, float y, float z, float* up, float* vp) { return (int)CamModelGeneral::GetCamera()->TransformRaysToCubemap(*up, *vp, x, y, z); }
+
+// the two matrix expressions every projection on the path goes through, evaluated by the cv:: shim (pinned against cv2.gemm in the tests):
+// `Rcw*x3Dw+tcw` (src/ORBMatcher.cpp:161, src/Frame.cpp:205) and `-Rcw.t()*tcw` (src/ORBMatcher.cpp:144, src/Frame.cpp:194)
+void ref_expr_Rx_plus_t(const float* R9, const float* x3, const float* t3, float* out3) {
+    cv::Mat R(3, 3, CV_32F, (void*)R9), x(3, 1, CV_32F, (void*)x3), t(3, 1, CV_32F, (void*)t3);
+    cv::Mat o = R * x + t;
+    for (int i = 0; i < 3; i++) out3[i] = o.at<float>(i);
+}
+void ref_expr_neg_Rt_t(const float* R9, const float* t3, float* out3) {
+    cv::Mat R(3, 3, CV_32F, (void*)R9), t(3, 1, CV_32F, (void*)t3);
+    cv::Mat o = -R.t() * t;
+    for (int i = 0; i < 3; i++) out3[i] = o.at<float>(i);
+}
+
 // ORBMatcher::DescriptorDistance, src/ORBMatcher.cpp:951-967
 int ref_descriptor_distance(const uint8_t* a, const uint8_t* b) {
     cv::Mat ma(1, 32, CV_8UC1, (void*)a), mb(1, 32, CV_8UC1, (void*)b);

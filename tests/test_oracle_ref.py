@@ -124,3 +124,19 @@ def test_descriptor_distance_kat(oracle, lafida):
     for _ in range(200):
         a = rng.integers(0, 256, 32, dtype=np.uint8); b = rng.integers(0, 256, 32, dtype=np.uint8)
         assert r.descriptor_distance(a, b) == oracle.descriptor_distance(a, b) == int(np.unpackbits(a ^ b).sum())
+
+
+def test_shim_gemm_matches_cv2(lafida):
+    """`R*x+t` and `-R.t()*t` as evaluated by the cv:: shim under the compiled reference == cv2.gemm 4.13 (small-matrix float path /
+    transposed double path); every projection of the matcher path goes through these two expressions."""
+    cv2 = pytest.importorskip("cv2")
+    cfg, cp, mask, maps = lafida
+    L = ref.Ref(cp).L
+    rng = np.random.default_rng(0)
+    for _ in range(3000):
+        R = rng.normal(0, 1, (3, 3)).astype(np.float32); x = rng.normal(0, 5, (3, 1)).astype(np.float32); t = rng.normal(0, 3, (3, 1)).astype(np.float32)
+        o = np.zeros(3, np.float32)
+        L.ref_expr_Rx_plus_t(ref._p(R), ref._p(x), ref._p(t), ref._p(o))
+        assert np.array_equal(o, cv2.gemm(R, x, 1.0, t, 1.0)[:, 0])
+        L.ref_expr_neg_Rt_t(ref._p(R), ref._p(t), ref._p(o))
+        assert np.array_equal(o, cv2.gemm(R, t, -1.0, None, 0.0, flags=cv2.GEMM_1_T)[:, 0])
