@@ -151,6 +151,12 @@ int orc_search_by_projection_local(void* hv, const uint8_t* dF, const float* sca
     GridHandle* h = (GridHandle*)hv;
     return fi_search_by_projection_local(h->g, h->kps.data(), dF, (int)h->kps.size(), scaleFactors, nMP, inView, projXY, level, viewCos, dMP, mpObs, fTaken, th, nnratio, matchF);
 }
+int orc_area_rects(float x, float y, float r, int faceW, int faceH, int* rects) {
+    FiRect rc[3]; const float inv = static_cast<float>(3 * FI_G) / static_cast<float>((float)(3 * faceW) - 0.0f);
+    const int n = fi_area_rects(x, y, r, faceW, faceH, inv, rc);
+    for (int k = 0; k < n; k++) { rects[5 * k] = rc[k].face; rects[5 * k + 1] = rc[k].x0; rects[5 * k + 2] = rc[k].x1; rects[5 * k + 3] = rc[k].y0; rects[5 * k + 4] = rc[k].y1; }
+    return n;
+}
 void orc_ray_to_cubemap(const float* xyz, int n, int faceW, int faceH, float* uv, int* faces) {
     for (int i = 0; i < n; i++) faces[i] = fi_ray_to_cubemap(xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2], faceW, faceH, uv[2 * i], uv[2 * i + 1]);
 }

@@ -272,6 +272,12 @@ class FrameGrid:
         return n, match
 
 
+def area_rects(x, y, r, faceW, faceH):
+    out = np.zeros((3, 5), np.int32)
+    n = lib().orc_area_rects(C.c_float(x), C.c_float(y), C.c_float(r), int(faceW), int(faceH), _p(out))
+    return out[:n].copy()
+
+
 def ray_to_cubemap(xyz, faceW, faceH):
     xyz = _f32(xyz).reshape(-1, 3); n = len(xyz)
     uv = np.zeros((n, 2), np.float32); faces = np.zeros(n, np.int32)
