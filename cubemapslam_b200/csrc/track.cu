@@ -310,7 +310,7 @@ __global__ void __launch_bounds__(TRK_WARPS * 32) k_search_by_projection(TrackAr
         }
         __syncthreads();
         for (int i = tid; i < logN; i += blockDim.x)
-            if (!keep[logBin[i]]) { M[logIdx[i]] = -1; atomicSub(&total, 1); }
+            if (!keep[logBin[i]]) { M[logIdx[i]] = -2; atomicSub(&total, 1); }   // -2: assigned, then cleared (the reference NULLs the slot)
         __syncthreads();
     }
     if (tid == 0) A.nmatches[p] = total;

@@ -154,7 +154,8 @@ int cslam_frame_index_dev(cslam_tracker* t, const cslam_keypoint* kps, const int
 int cslam_area_rects(float x, float y, float r, int face_w, int face_h, int32_t* rects);
 /* has_mp: LastFrame.mvpMapPoints[i] != NULL && !mvbOutlier[i]; Xw / d_mp: that MapPoint's GetWorldPos() / GetDescriptor(); mp_obs: Observations() > 0;
  * cur_taken: CurrentFrame.mvpMapPoints[i2] holds a MapPoint with Observations() > 0 before the call; cos_fov_th: CamModelGeneral::GetCosFovTh().
- * match_cur: npairs x cur_stride, index of the LastFrame feature whose MapPoint is assigned to the slot, or -1. nmatches: the function's return value. */
+ * match_cur: npairs x cur_stride, index of the LastFrame feature whose MapPoint is assigned to the slot; -1 = slot untouched; -2 = assigned and then cleared by
+ * the rotation-consistency filter (the reference sets the slot to NULL). nmatches: the function's return value. */
 int cslam_search_by_projection_last(cslam_tracker* t, int npairs, const cslam_keypoint* k_cur, const uint8_t* d_cur, const int32_t* n_cur, int cur_stride,
                                     const uint8_t* cur_taken, const float* Tcw_cur, const cslam_keypoint* k_last, const int32_t* n_last, int last_stride,
                                     const uint8_t* has_mp, const float* Xw, const uint8_t* d_mp, const uint8_t* mp_obs, int face_w, int face_h, float cos_fov_th, float th,

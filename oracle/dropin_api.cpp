@@ -7,7 +7,7 @@
 //     Optimizer::PoseOptimization(&mCurrentFrame)                                          src/Tracking.cpp:585,647,688
 //     Optimizer::LocalBundleAdjustment(mpCurrentKeyFrame, &mbAbortBA, mpMap)               src/LocalMapping.cpp:86
 // run unchanged against libcubemap_b200.so. The reference's own src/ORBMatcher.cpp is linked too, with the replaced method renamed
-// (-DSearchByBoW=SearchByBoW_cpu, see oracle/Makefile) so the same objects can be matched by the reference's CPU code for comparison.
+// (-DSearchByBoW=SearchByBoW_cpu -DSearchByProjection=SearchByProjection_cpu, see oracle/Makefile) so the same objects can be matched by the reference's CPU code for comparison.
 #include <cstring>
 #include <map>
 #include <vector>
@@ -33,7 +33,10 @@ std::vector<cv::Mat> Converter::toDescriptorVector(const cv::Mat& Descriptors) {
 // the out-of-scope optimisations declared by include/Optimizer.h are never called by the harness
 // (src/Optimizer.cpp needs g2o / Eigen and is not part of this library)
 
-int call_cpu_search_by_bow(KeyFrame* pKF, Frame& F, std::vector<MapPoint*>& v, float nnratio, bool ori);   // dropin_cpu_calls.cpp
+// the reference's own CPU bodies on the same objects (dropin/ORBMatcher_cpu_forward.cpp)
+int cslam_cpu_SearchByBoW(ORBMatcher* m, KeyFrame* pKF, Frame& F, std::vector<MapPoint*>& vpMapPointMatches);
+int cslam_cpu_SearchByProjection(ORBMatcher* m, Frame& CurrentFrame, const Frame& LastFrame, const float th, const bool bMono);
+int cslam_cpu_SearchByProjection(ORBMatcher* m, Frame& F, const std::vector<MapPoint*>& vpMapPoints, const float th);
 
 struct RefCam { double c, d, e, u0, v0, p[5], invp[12]; int Iw, Ih, faceW, faceH; double fov; };
 
@@ -61,6 +64,17 @@ Frame* make_frame(int n, const KpPOD* kps, const uint8_t* desc, const float* Tcw
     for (int i = 0; i < nlevels; i++) { F->mvInvScaleFactors[i] = 1.0f / F->mvScaleFactors[i]; F->mvInvLevelSigma2[i] = 1.0f / F->mvLevelSigma2[i]; }
     if (Tcw) F->SetPose(mat_from(Tcw, 4, 4));
     return F;
+}
+// Frame::AssignFeaturesToGrid is private: replay it (src/Frame.cpp:158-176) with the public PosInGrid
+void build_grid(Frame* F) {
+    const int W3 = 3 * CamModelGeneral::GetCamera()->GetCubeFaceWidth();
+    Frame::mnMinX = 0.0f; Frame::mnMaxX = (float)W3; Frame::mnMinY = 0.0f; Frame::mnMaxY = (float)(3 * CamModelGeneral::GetCamera()->GetCubeFaceHeight());
+    Frame::mfGridElementLengthInv = static_cast<float>(3 * CUBEFACE_GRID_COLS) / static_cast<float>(Frame::mnMaxX - Frame::mnMinX);
+    Frame::mfGridElementLength = static_cast<float>(Frame::mnMaxX - Frame::mnMinX) / static_cast<float>(3 * CUBEFACE_GRID_COLS);
+    for (int i = 0; i < F->N; i++) {
+        CamModelGeneral::eFace face; int gx, gy;
+        if (F->PosInGrid(F->mvKeys[i], face, gx, gy)) F->mGrid[face][gx][gy].push_back(i);
+    }
 }
 void fill_featvec(DBoW2::FeatureVector& fv, const int32_t* node, int n) { for (int i = 0; i < n; i++) if (node[i] >= 0) fv.addFeature((DBoW2::NodeId)node[i], (unsigned)i); }
 }  // namespace
@@ -116,10 +130,45 @@ void dropin_search_by_bow(int nKF, const KpPOD* kpK, const uint8_t* descK, const
     ORBMatcher matcher(nnratio, checkOri != 0);
     *nGpu = matcher.SearchByBoW(pKF, *F, out);                              // dropin/ORBMatcher_b200.cpp -> libcubemap_b200.so
     for (int j = 0; j < nF; j++) matchGpu[j] = out[j] ? idxOf[out[j]] : -1;
-    *nCpu = call_cpu_search_by_bow(pKF, *F, out, nnratio, checkOri != 0);   // the reference's src/ORBMatcher.cpp:409-539
+    *nCpu = cslam_cpu_SearchByBoW(&matcher, pKF, *F, out);                  // the reference's src/ORBMatcher.cpp:409-539
     for (int j = 0; j < nF; j++) matchCpu[j] = out[j] ? idxOf[out[j]] : -1;
     for (std::map<MapPoint*, int>::iterator it = idxOf.begin(); it != idxOf.end(); ++it) delete it->first;
     delete pKF; delete FK; delete F;
+}
+
+// ORBMatcher(0.9, checkOri).SearchByProjection(CurrentFrame, LastFrame, th, true) (src/Tracking.cpp:634) on reference Frame / MapPoint objects:
+// GPU drop-in and the reference's CPU body from identical starting states. match*[i2]: LastFrame feature index now in the slot, -1 empty, -2 a
+// pre-existing MapPoint that was left alone.
+void dropin_search_by_projection_last(int nCur, const KpPOD* kCur, const uint8_t* dCur, const float* TcwCur, int nLast, const KpPOD* kLast, const float* TcwLast,
+                                      const uint8_t* hasMP, const float* Xw, const uint8_t* dMP, const int32_t* mpObs, const uint8_t* curTaken, float th, int checkOri,
+                                      int32_t* matchGpu, int32_t* nGpu, int32_t* matchCpu, int32_t* nCpu) {
+    Map map;
+    Frame* last = make_frame(nLast, kLast, dMP, TcwLast, 8, 1.2f);
+    KeyFrame* kfObs = new KeyFrame(*last, &map, NULL);
+    std::map<MapPoint*, int> idxOf; std::vector<MapPoint*> owned;
+    for (int i = 0; i < nLast; i++) {
+        if (!hasMP[i]) continue;
+        MapPoint* mp = new MapPoint(mat_from(Xw + 3 * i, 3, 1), &map, last, i);
+        if (mpObs[i] > 0) mp->AddObservation(kfObs, i);
+        last->mvpMapPoints[i] = mp; idxOf[mp] = i; owned.push_back(mp);
+    }
+    const float P0[3] = {0, 0, 1};
+    std::vector<MapPoint*> pre(nCur, static_cast<MapPoint*>(NULL));
+    for (int i2 = 0; i2 < nCur; i2++) if (curTaken[i2]) { pre[i2] = new MapPoint(mat_from(P0, 3, 1), kfObs, &map); pre[i2]->AddObservation(kfObs, 0); idxOf[pre[i2]] = -2; owned.push_back(pre[i2]); }
+    for (int pass = 0; pass < 2; pass++) {
+        Frame* cur = make_frame(nCur, kCur, dCur, TcwCur, 8, 1.2f);
+        build_grid(cur);
+        for (int i2 = 0; i2 < nCur; i2++) cur->mvpMapPoints[i2] = pre[i2];
+        ORBMatcher matcher(0.9f, checkOri != 0);
+        int32_t* out = pass == 0 ? matchGpu : matchCpu;
+        const int n = pass == 0 ? matcher.SearchByProjection(*cur, *last, th, true)              // dropin/ORBMatcher_b200.cpp -> libcubemap_b200.so
+                                : cslam_cpu_SearchByProjection(&matcher, *cur, *last, th, true);   // src/ORBMatcher.cpp:130-251
+        (pass == 0 ? *nGpu : *nCpu) = n;
+        for (int i2 = 0; i2 < nCur; i2++) out[i2] = cur->mvpMapPoints[i2] ? idxOf[cur->mvpMapPoints[i2]] : -1;
+        delete cur;
+    }
+    for (MapPoint* mp : owned) delete mp;
+    delete kfObs; delete last;
 }
 
 // Optimizer::PoseOptimization(&frame): n correspondences (keypoint, octave, world point). Returns inliers; Tcw in/out; outlier[n] = mvbOutlier.

@@ -101,3 +101,26 @@ def test_local_bundle_adjustment_on_reference_map(oracle, dropin):
     assert r["iters"] >= 5
     assert np.array_equal(erased, r["outlier"])
     assert np.allclose(T.reshape(nKF, 4, 4), r["Tcw"], atol=2e-6) and np.allclose(pts, r["pts"], atol=2e-6)
+
+
+@pytest.mark.parametrize("seed,th", [(0, 15.0), (1, 30.0)])
+def test_search_by_projection_on_reference_frames(oracle, seed, th):
+    """ORBMatcher(0.9, true).SearchByProjection(CurrentFrame, LastFrame, th, true) (src/Tracking.cpp:634) on reference Frame / MapPoint objects:
+    the GPU drop-in and the reference's own CPU body, from identical starting states, leave identical mvpMapPoints and return the same count."""
+    if not os.path.exists(LIB):
+        pytest.skip("oracle/_ref/libdropin.so is built in the build container")
+    L = C.CDLL(LIB)
+    cp = oracle.cam_params(config.front_1024())
+    L.dropin_set_camera(C.byref(cp))
+    s = synth.tracking_pair(seed, n=1500, faceW=650)
+    nC, nL = len(s["kCur"]), len(s["kLast"])
+    mg = np.zeros(nC, np.int32); mc = np.zeros(nC, np.int32); ng = C.c_int32(); nc = C.c_int32()
+    arrs = [np.ascontiguousarray(s["kCur"]), np.ascontiguousarray(s["dCur"]), np.ascontiguousarray(s["TcwCur"], np.float32), np.ascontiguousarray(s["kLast"]),
+            np.ascontiguousarray(s["TcwLast"], np.float32), np.ascontiguousarray(s["hasMP"]), np.ascontiguousarray(s["Xw"]), np.ascontiguousarray(s["dLast"]),
+            np.ascontiguousarray(s["mpObs"], np.int32), np.ascontiguousarray(s["curTaken"])]
+    L.dropin_search_by_projection_last(nC, _p(arrs[0]), _p(arrs[1]), _p(arrs[2]), nL, _p(arrs[3]), _p(arrs[4]), _p(arrs[5]), _p(arrs[6]), _p(arrs[7]), _p(arrs[8]), _p(arrs[9]),
+                                       C.c_float(th), 1, _p(mg), C.byref(ng), _p(mc), C.byref(nc))
+    assert ng.value == nc.value > 300
+    assert np.array_equal(mg, mc)
+    # fixture switches the singleton camera back for the other tests of this module
+    L.dropin_set_camera(C.byref(oracle.cam_params(config.lafida_450())))
