@@ -49,18 +49,23 @@ __device__ __forceinline__ int hamming256(const uint32_t (&a)[8], const uint4 b0
            __popc(a[4] ^ b1.x) + __popc(a[5] ^ b1.y) + __popc(a[6] ^ b1.z) + __popc(a[7] ^ b1.w);
 }
 
-__global__ void __launch_bounds__(BF_THREADS) k_match_bruteforce(const uint8_t* __restrict__ descA, const float* __restrict__ angA, int nA,
-                                                                 const uint8_t* __restrict__ descB, const float* __restrict__ angB, int nB, float nnratio,
+// Layout: pair p reads rows [p*strideA, p*strideA + nA) of descA (and B likewise); angles are read with a stride of `angStride` floats
+// (1 for a plain float array, 7 for cv::KeyPoint records, whose `angle` field the pointer then addresses); when nAarr / nBarr are given they
+// hold per-pair row counts (the front end's n_out). Outputs are strided like A.
+struct BfLayout { int strideA, strideB, angStride; const int32_t* nAarr; const int32_t* nBarr; };
+__global__ void __launch_bounds__(BF_THREADS) k_match_bruteforce(const uint8_t* __restrict__ descA, const float* __restrict__ angA, int nA_,
+                                                                 const uint8_t* __restrict__ descB, const float* __restrict__ angB, int nB_, float nnratio,
                                                                  int thLow, int checkOri, int32_t* __restrict__ match12, int32_t* __restrict__ dist12,
-                                                                 int32_t* __restrict__ second12, int32_t* __restrict__ nmatches) {
+                                                                 int32_t* __restrict__ second12, int32_t* __restrict__ nmatches, BfLayout L) {
     __shared__ __align__(16) uint4 sB[2 * BF_TILE];
     __shared__ int hist[HISTO_BINS], keep[HISTO_BINS], total;
     const int pair = blockIdx.x, tid = threadIdx.x;
-    const uint4* A4 = reinterpret_cast<const uint4*>(descA + (size_t)pair * nA * 32);
-    const uint4* B4 = reinterpret_cast<const uint4*>(descB + (size_t)pair * nB * 32);
-    const float* aA = angA + (size_t)pair * nA;
-    const float* aB = angB + (size_t)pair * nB;
-    int32_t* m12 = match12 + (size_t)pair * nA;
+    const int nA = L.nAarr ? min(L.nAarr[pair], L.strideA) : nA_, nB = L.nBarr ? min(L.nBarr[pair], L.strideB) : nB_;
+    const uint4* A4 = reinterpret_cast<const uint4*>(descA + (size_t)pair * L.strideA * 32);
+    const uint4* B4 = reinterpret_cast<const uint4*>(descB + (size_t)pair * L.strideB * 32);
+    const float* aA = angA + (size_t)pair * L.strideA * L.angStride;
+    const float* aB = angB + (size_t)pair * L.strideB * L.angStride;
+    int32_t* m12 = match12 + (size_t)pair * L.strideA;
     if (tid < HISTO_BINS) hist[tid] = 0;
     if (tid == 0) total = 0;
     __syncthreads();
@@ -90,12 +95,12 @@ __global__ void __launch_bounds__(BF_THREADS) k_match_bruteforce(const uint8_t* 
             int m = -1;
             if (bestIdx >= 0 && best1 <= thLow && (float)best1 < __fmul_rn(nnratio, (float)best2)) {
                 m = bestIdx;
-                if (checkOri) atomicAdd(&hist[rot_bin(aA[i], aB[bestIdx])], 1);
+                if (checkOri) atomicAdd(&hist[rot_bin(aA[(size_t)i * L.angStride], aB[(size_t)bestIdx * L.angStride])], 1);
                 atomicAdd(&total, 1);
             }
             m12[i] = m;
-            if (dist12) dist12[(size_t)pair * nA + i] = best1;
-            if (second12) second12[(size_t)pair * nA + i] = best2;
+            if (dist12) dist12[(size_t)pair * L.strideA + i] = best1;
+            if (second12) second12[(size_t)pair * L.strideA + i] = best2;
         }
     }
     __syncthreads();
@@ -104,7 +109,7 @@ __global__ void __launch_bounds__(BF_THREADS) k_match_bruteforce(const uint8_t* 
         __syncthreads();
         for (int i = tid; i < nA; i += BF_THREADS) {
             const int m = m12[i];
-            if (m >= 0 && !keep[rot_bin(aA[i], aB[m])]) { m12[i] = -1; atomicSub(&total, 1); }
+            if (m >= 0 && !keep[rot_bin(aA[(size_t)i * L.angStride], aB[(size_t)m * L.angStride])]) { m12[i] = -1; atomicSub(&total, 1); }
         }
         __syncthreads();
     }
@@ -310,7 +315,8 @@ extern "C" int cslam_match_bruteforce_dev(cslam_matcher* m, const uint8_t* descA
     int rc = check_sizes(m, nA, nB, npairs);
     if (rc) return rc;
     if (nA == 0) { CSLAM_CUDA(cudaMemsetAsync(nmatches, 0, (size_t)npairs * 4, m->stream)); return CSLAM_OK; }
-    k_match_bruteforce<<<npairs, BF_THREADS, 0, m->stream>>>(descA, angA, nA, descB, angB, nB, nnratio, th_low, check_ori, match12, dist12, second12, nmatches);
+    const BfLayout L = {nA, nB, 1, nullptr, nullptr};
+    k_match_bruteforce<<<npairs, BF_THREADS, 0, m->stream>>>(descA, angA, nA, descB, angB, nB, nnratio, th_low, check_ori, match12, dist12, second12, nmatches, L);
     m->launches++;
     CSLAM_CUDA(cudaGetLastError());
     return CSLAM_OK;
@@ -332,6 +338,57 @@ extern "C" int cslam_match_bruteforce(cslam_matcher* m, const uint8_t* descA, co
     }
     CSLAM_CUDA(cudaMemcpyAsync(nmatches, m->dN, (size_t)npairs * 4, cudaMemcpyDeviceToHost, m->stream));
     CSLAM_CUDA(cudaStreamSynchronize(m->stream));
+    return CSLAM_OK;
+}
+
+// All-pairs matcher between consecutive frames of a front-end batch, straight from cslam_frontend_run_dev's output layout: frame f (rows
+// [f*kp_stride, f*kp_stride + n[f]) of kps / desc) is matched against frame f+1 for f = 0 .. nframes-2. match12: (nframes-1) x kp_stride.
+extern "C" int cslam_match_frames_dev(cslam_matcher* m, const cslam_keypoint* kps, const uint8_t* desc, const int32_t* n, int kp_stride, int nframes, float nnratio, int th_low,
+                                      int check_ori, int32_t* match12, int32_t* nmatches) {
+    if (!m || !kps || !desc || !n || !match12 || !nmatches || nframes < 2 || kp_stride <= 0) { set_error("cslam_match_frames_dev: bad argument"); return CSLAM_E_BADARG; }
+    CSLAM_CUDA(cudaSetDevice(m->device));
+    const float* ang = &kps[0].angle;
+    const BfLayout L = {kp_stride, kp_stride, (int)(sizeof(cslam_keypoint) / sizeof(float)), n, n + 1};
+    k_match_bruteforce<<<nframes - 1, BF_THREADS, 0, m->stream>>>(desc, ang, 0, desc + (size_t)kp_stride * 32, ang + (size_t)kp_stride * L.angStride, 0, nnratio, th_low, check_ori,
+                                                                   match12, nullptr, nullptr, nmatches, L);
+    m->launches++;
+    CSLAM_CUDA(cudaGetLastError());
+    return CSLAM_OK;
+}
+
+// POPC issue-rate micro-benchmark ("measure the real rate with a micro-benchmark on the box before quoting a fraction"): every thread
+// runs `iters` rounds of 8 independent XOR+POPC+ADD chains on registers - the exact instruction mix of hamming256 without any memory traffic.
+__global__ void __launch_bounds__(256) k_ubench_popc(uint32_t* out, int iters, uint32_t seed) {
+    uint32_t a[8], acc[8];
+#pragma unroll
+    for (int k = 0; k < 8; k++) { a[k] = seed * (threadIdx.x + 1) + k * 0x9e3779b9u + blockIdx.x; acc[k] = 0; }
+    for (int i = 0; i < iters; i++) {
+#pragma unroll
+        for (int k = 0; k < 8; k++) { acc[k] += __popc(a[k] ^ acc[(k + 1) & 7]); }
+    }
+    uint32_t s = 0;
+#pragma unroll
+    for (int k = 0; k < 8; k++) s += acc[k];
+    if (s == 0xdeadbeefu) out[0] = s;   // keeps the chains alive
+}
+extern "C" int cslam_ubench_popc(cslam_matcher* m, double* popc32_per_s) {
+    if (!m || !popc32_per_s) return CSLAM_E_BADARG;
+    CSLAM_CUDA(cudaSetDevice(m->device));
+    int sms = 148;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, m->device);
+    const int blocks = sms * 8, iters = 20000;
+    cudaEvent_t e0, e1;
+    CSLAM_CUDA(cudaEventCreate(&e0)); CSLAM_CUDA(cudaEventCreate(&e1));
+    k_ubench_popc<<<blocks, 256, 0, m->stream>>>(reinterpret_cast<uint32_t*>(m->dN), 100, 1u);   // warm-up
+    CSLAM_CUDA(cudaEventRecord(e0, m->stream));
+    k_ubench_popc<<<blocks, 256, 0, m->stream>>>(reinterpret_cast<uint32_t*>(m->dN), iters, 1u);
+    CSLAM_CUDA(cudaEventRecord(e1, m->stream));
+    CSLAM_CUDA(cudaStreamSynchronize(m->stream));
+    float ms = 0;
+    CSLAM_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    m->launches += 2;
+    *popc32_per_s = (double)blocks * 256.0 * iters * 8.0 / (ms * 1e-3);
     return CSLAM_OK;
 }
 

@@ -72,6 +72,15 @@ class ORBMatcher:
         check(lib().cslam_match_bruteforce_dev(self._h, ptr(descA), ptr(angA), int(nA), ptr(descB), ptr(angB), int(nB), int(npairs), C.c_float(self.nnratio),
                                                int(th_low), int(self.check_ori), ptr(match12), ptr(dist12), ptr(second12), ptr(nmatches)))
 
+    def match_frames_dev(self, kps, desc, n, kp_stride, nframes, match12, nmatches, th_low=TH_LOW):
+        check(lib().cslam_match_frames_dev(self._h, ptr(kps), ptr(desc), ptr(n), int(kp_stride), int(nframes), C.c_float(self.nnratio), int(th_low), int(self.check_ori),
+                                           ptr(match12), ptr(nmatches)))
+
+    def ubench_popc(self):
+        v = C.c_double()
+        check(lib().cslam_ubench_popc(self._h, C.byref(v)))
+        return v.value
+
     def SearchByBoW(self, descKF, angKF, kf_valid, node_kf, descF, angF, node_f):
         a = [np.ascontiguousarray(descKF, np.uint8), np.ascontiguousarray(angKF, np.float32), np.ascontiguousarray(kf_valid, np.uint8),
              np.ascontiguousarray(node_kf, np.int32), np.ascontiguousarray(descF, np.uint8), np.ascontiguousarray(angF, np.float32),

@@ -112,6 +112,13 @@ int cslam_match_bruteforce(cslam_matcher* m, const uint8_t* descA, const float* 
 int cslam_match_bruteforce_dev(cslam_matcher* m, const uint8_t* descA, const float* angA, int nA, const uint8_t* descB,
                                const float* angB, int nB, int npairs, float nnratio, int th_low, int check_ori,
                                int32_t* match12, int32_t* dist12, int32_t* second12, int32_t* nmatches);
+/* The same matcher between consecutive frames of a front-end batch, reading cslam_frontend_run_dev's output layout directly (device pointers,
+ * asynchronous): frame f is matched against frame f+1, f = 0 .. nframes-2; kp_stride = cslam_frontend_kp_capacity; n = the front end's n_out. */
+int cslam_match_frames_dev(cslam_matcher* m, const cslam_keypoint* kps, const uint8_t* desc, const int32_t* n, int kp_stride, int nframes, float nnratio, int th_low,
+                           int check_ori, int32_t* match12, int32_t* nmatches);
+/* Measured POPC issue rate of this GPU (32-bit population counts per second with the XOR+POPC+ADD mix of the Hamming kernels, no memory traffic):
+ * the ceiling the matcher's roofline fraction is quoted against (bench.py). */
+int cslam_ubench_popc(cslam_matcher* m, double* popc32_per_s);
 /* ORBMatcher::SearchByBoW(KeyFrame*, Frame&, vector<MapPoint*>&) (src/ORBMatcher.cpp:409-539) for npairs (KF,F) pairs.
  * kf_valid: 1 where the KF feature has a good MapPoint; node_kf/node_f: DBoW2 FeatureVector node id per feature.
  * match_f: npairs x nF (index of the KF feature whose MapPoint is assigned, or -1); nmatches: npairs. */

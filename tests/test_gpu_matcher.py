@@ -106,3 +106,32 @@ def test_search_by_bow_keyframe_pair(oracle):
     assert got_n == ref_n and np.array_equal(got, ref) and ref_n > 200
     assert np.all(v2[got[got >= 0]] == 1) and np.all(v1[got >= 0] == 1)
     m.close()
+
+
+def test_match_consecutive_frames_from_frontend_layout(oracle):
+    """cslam_match_frames_dev: frame f vs f+1 straight from the front end's device output (ragged counts, cv::KeyPoint angle stride)."""
+    import torch
+    from cubemapslam_b200 import config
+    from cubemapslam_b200.frontend import FrontEnd
+    from cubemapslam_b200.matcher import ORBMatcher
+    cfg = config.lafida_450(); mask = config.load_mask("gray_lafida_cubemap_mask_450")
+    fe = FrontEnd(cfg, mask, max_batch=3)
+    frames = np.stack([synth.fisheye_frame(cfg, i) for i in (0, 1, 2)])
+    frames[1] = np.roll(frames[0], 3, axis=1)                      # frame 1 ~ frame 0 shifted: plenty of true matches
+    dev = torch.device("cuda", 0)
+    cap = fe.kp_cap
+    fish = torch.from_numpy(frames).to(dev)
+    kps = torch.zeros((3, cap, 28), dtype=torch.uint8, device=dev); desc = torch.zeros((3, cap, 32), dtype=torch.uint8, device=dev); n = torch.zeros(3, dtype=torch.int32, device=dev)
+    fe.run_dev(fish.data_ptr(), 3, kps.data_ptr(), desc.data_ptr(), n.data_ptr()); fe.sync()
+    m = ORBMatcher(0.8, True, max_pairs=2, max_features=cap)
+    match = torch.full((2, cap), -7, dtype=torch.int32, device=dev); nm = torch.zeros(2, dtype=torch.int32, device=dev)
+    fs = torch.cuda.ExternalStream(fe.stream, device=dev); ms = torch.cuda.ExternalStream(m.stream, device=dev); ms.wait_stream(fs)
+    m.match_frames_dev(kps.data_ptr(), desc.data_ptr(), n.data_ptr(), cap, 3, match.data_ptr(), nm.data_ptr()); m.sync()
+    hk = kps.cpu().numpy().view(np.dtype([("x", "<f4"), ("y", "<f4"), ("size", "<f4"), ("angle", "<f4"), ("response", "<f4"), ("octave", "<i4"), ("class_id", "<i4")])).reshape(3, cap)
+    hd = desc.cpu().numpy(); hn = n.cpu().numpy(); hm = match.cpu().numpy(); hnm = nm.cpu().numpy()
+    for f in range(2):
+        a, b = hn[f], hn[f + 1]
+        rn, rm, rd, rs = oracle.match_bruteforce(hd[f, :a], hk[f, :a]["angle"], hd[f + 1, :b], hk[f + 1, :b]["angle"], 0.8, 50, True)
+        assert hnm[f] == rn and np.array_equal(hm[f, :a], rm), f
+    assert hnm[0] > 300
+    m.close(); fe.close()
