@@ -1,14 +1,15 @@
 #!/usr/bin/env python
-"""bench.py — headline benchmark of the B200 hot path (BASELINE.json metric).
+"""bench.py — headline benchmark of the B200 hot path (BASELINE.json metric: "frames/sec ORB extract+match & LocalBA iters/sec").
 
   python bench.py --gpus N --steps K --warmup W            # our arm (one process per GPU under torchrun for N>1)
-  python bench.py --impl reference --gpus N --steps K ...  # the reference's CPU path (oracle port) on the host cores
+  python bench.py --impl reference --gpus N --steps K ...  # the reference's CPU path on the host cores
 
-Workload at N=1 = BASELINE.json configs[1]: batched fisheye->cubemap warp + ORB extraction of 4096 synthetic
-1280x1024 frames, 650-px faces (front_cam_params.yaml with Ih=1024, nFeatures 3000). A "step" is one pass over all
-4096 frames (launched in batches of --batch). Frames are sharded over ranks without any collective; per-rank work is
-fixed ("weak" scaling), `value` is the whole-job frames/s = N * frames * K / max-over-ranks device time.
-Extra legs (matching pairs/s, LocalBA LM iterations/s) are reported under "extra" in the same JSON line.
+Workload at N=1 = BASELINE.json configs[1] (+ the matching of configs[2] on the extracted descriptors): batched fisheye->cubemap warp + ORB
+extraction of 4096 synthetic 1280x1024 frames, 650-px faces (front_cam_params.yaml with Ih=1024, nFeatures 3000), then the all-pairs 256-bit
+Hamming matcher between every pair of consecutive frames. A "step" is one pass over all 4096 frames (launched in batches of --batch).
+Frames are sharded over ranks without any collective; per-rank work is fixed ("weak" scaling), `value` is the whole-job frames/s =
+N * frames * K / max-over-ranks device time. LocalBA LM iterations/s (configs[3], the second half of the metric), the 2000x2000 matcher
+of configs[2], PoseOptimization and the config-5 tracking pipeline are separate legs under "extra", each with its own roofline / cpu_baseline / e2e.
 """
 import argparse
 import json
@@ -26,10 +27,10 @@ sys.path.insert(0, ROOT)
 from cubemapslam_b200 import config, synth  # noqa: E402
 
 N_BASE = 16          # distinct synthetic frames generated with the SURVEY §8d recipe; the rest are circular shifts of them
+METRIC = "warp+ORB-extract+match frames/sec"
 
 
 def load_mask():
-    import cv2
     return config.load_mask("gray_cubemap_front_mask_650")
 
 
@@ -37,8 +38,8 @@ def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
         d = json.load(open(p))
-        return d.get("hbm_gbs", 6650.0), d.get("bf16_tflops", 1590.0), "measured"
-    return 6650.0, 1590.0, "fallback"
+        return d.get("hbm_gbs", 6650.0), d.get("bf16_tflops", 1590.0), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, 1590.0, "fallback (B200_PROFILING.md)"
 
 
 class ClockSampler:
@@ -84,13 +85,12 @@ class ClockSampler:
 
 def make_frames_device(torch, cfg, frames, device):
     """frames x Ih x Iw uint8 on the device: N_BASE recipe frames, the others are horizontal rolls re-masked by the image circle."""
+    import math
     Iw, Ih = int(cfg["Camera.Iw"]), int(cfg["Camera.Ih"])
     base = np.stack([synth.fisheye_frame(cfg, i) for i in range(min(N_BASE, frames))])
     tb = torch.from_numpy(base).to(device)
-    circle = torch.from_numpy((synth.fisheye_frame(cfg, 0) > 0) | (base[0] > 0)).to(device)   # support of the image circle
     yy, xx = np.mgrid[0:Ih, 0:Iw]
     invp = [cfg.get("Camera.pol%d" % i, 0.0) for i in range(int(cfg["Camera.nrinvpol"]))]
-    import math
     fov = cfg["Camera.fov"] / 2.0 * math.pi / 180.0
     rho = synth._horner(invp, math.atan(-math.cos(fov) / math.sin(fov)))
     circle = torch.from_numpy(((xx - cfg["Camera.u0"]) ** 2 + (yy - cfg["Camera.v0"]) ** 2 <= rho ** 2)).to(device)
@@ -116,7 +116,7 @@ def geometry_bytes(cfg, nlevels=8, scale=1.2):
 def run_ours(args):
     import torch
     from cubemapslam_b200.frontend import FrontEnd
-    from cubemapslam_b200 import _capi
+    from cubemapslam_b200.matcher import ORBMatcher
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback")
@@ -129,20 +129,29 @@ def run_ours(args):
     mask = load_mask()
     B = args.batch
     fe = FrontEnd(cfg, mask, max_batch=B, device=local)
+    kp_cap = fe.kp_cap
+    mt = ORBMatcher(0.6, True, max_pairs=B + 1, max_features=kp_cap, device=local)
     frames = args.frames
     fish, base_host = make_frames_device(torch, cfg, frames, dev)
     fsz = fish.shape[1] * fish.shape[2]
-    kp_cap = fe.kp_cap
     kps = torch.empty((frames, kp_cap, 28), dtype=torch.uint8, device=dev)
     desc = torch.empty((frames, kp_cap, 32), dtype=torch.uint8, device=dev)
-    nout = torch.empty((frames,), dtype=torch.int32, device=dev)
-    stream = torch.cuda.ExternalStream(fe.stream, device=dev)
+    nout = torch.zeros((frames,), dtype=torch.int32, device=dev)
+    match = torch.empty((frames, kp_cap), dtype=torch.int32, device=dev)
+    nmatch = torch.zeros((frames,), dtype=torch.int32, device=dev)
+    fs = torch.cuda.ExternalStream(fe.stream, device=dev); ms = torch.cuda.ExternalStream(mt.stream, device=dev)
     torch.cuda.synchronize()
 
     def one_step():
+        fs.wait_stream(ms)                                          # the next pass overwrites buffers the matcher of the previous pass read
         for c in range(0, frames, B):
             b = min(B, frames - c)
             fe.run_dev(fish.data_ptr() + c * fsz, b, kps.data_ptr() + c * kp_cap * 28, desc.data_ptr() + c * kp_cap * 32, nout.data_ptr() + c * 4)
+            ms.wait_stream(fs)
+            f0 = max(c - 1, 0); nf = c + b - f0                     # pairs (f, f+1) whose second frame was just extracted
+            if nf >= 2:
+                mt.match_frames_dev(kps.data_ptr() + f0 * kp_cap * 28, desc.data_ptr() + f0 * kp_cap * 32, nout.data_ptr() + f0 * 4, kp_cap, nf,
+                                    match.data_ptr() + f0 * kp_cap * 4, nmatch.data_ptr() + f0 * 4)
 
     def barrier():
         torch.cuda.synchronize()
@@ -152,123 +161,137 @@ def run_ours(args):
 
     for _ in range(args.warmup):
         one_step()
-    fe.sync()
+    fe.sync(); mt.sync()
     barrier()
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    l0 = fe.launches
+    l0 = fe.launches + mt.launches
     e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
-    e0.record(stream)
+    e0.record(fs)
     for _ in range(args.steps):
         one_step()
-    e1.record(stream)
-    fe.sync()
+    ms.wait_stream(fs)
+    e1.record(ms)
+    fe.sync(); mt.sync()
     barrier()
-    ms = e0.elapsed_time(e1)
-    launches = fe.launches - l0
+    ms_total = e0.elapsed_time(e1)
+    launches = fe.launches + mt.launches - l0
     clocks = sampler.stop() if rank == 0 else None
-    tms = torch.tensor([ms], dtype=torch.float64, device=dev)
+    tms = torch.tensor([ms_total], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(tms, op=dist.ReduceOp.MAX)
     ms_max = float(tms.item())
     value = world * frames * args.steps / (ms_max / 1e3)
-    nkp = float(nout.float().mean().item())
+    nkp = float(nout.float().mean().item()); nmt = float(nmatch[:frames - 1].float().mean().item())
 
-    # ---- end-to-end through the reference-facing host call (pinned host frames in, host keypoints out)
+    # ---- end-to-end through the host entry points (pinned host frames in, host keypoints / descriptors / matches out)
     ef = min(args.e2e_frames, frames)
     h_in = torch.empty((ef, fish.shape[1], fish.shape[2]), dtype=torch.uint8).pin_memory()
     h_in.copy_(fish[:ef].cpu())
-    # page-locked result buffers: the library DMAs straight into caller memory when it is pinned
-    t_kps = torch.empty((B, kp_cap, 28), dtype=torch.uint8).pin_memory(); t_desc = torch.empty((B, kp_cap, 32), dtype=torch.uint8).pin_memory()
-    t_n = torch.empty((B,), dtype=torch.int32).pin_memory()
-    h_kps = t_kps.numpy(); h_desc = t_desc.numpy(); h_n = t_n.numpy()
-    h_np = h_in.numpy()
+    KP = np.dtype([("x", "<f4"), ("y", "<f4"), ("size", "<f4"), ("angle", "<f4"), ("response", "<f4"), ("octave", "<i4"), ("class_id", "<i4")])
+    t_kps = torch.empty((B + 1, kp_cap, 28), dtype=torch.uint8).pin_memory(); t_desc = torch.empty((B + 1, kp_cap, 32), dtype=torch.uint8).pin_memory()
+    t_n = torch.empty((B + 1,), dtype=torch.int32).pin_memory()
+    h_kps = t_kps.numpy(); h_desc = t_desc.numpy(); h_n = t_n.numpy(); h_np = h_in.numpy()
 
     def e2e_pass():
-        tot = 0
+        tot = 0; have_prev = False
         for c in range(0, ef, B):
             b = min(B, ef - c)
-            fe.run_raw(h_np[c:c + b], h_kps, h_desc, h_n)
-            tot += int(h_n[:b].sum())
+            # slot 0 keeps the last frame of the previous batch so that every consecutive pair is matched
+            fe.run_raw(h_np[c:c + b], h_kps[1:], h_desc[1:], h_n[1:])
+            lo = 0 if have_prev else 1
+            nm_, _m = mt.match_frames(h_kps[lo:b + 1].view(KP).reshape(b + 1 - lo, kp_cap), h_desc[lo:b + 1], h_n[lo:b + 1])
+            tot += int(nm_.sum())
+            h_kps[0] = h_kps[b]; h_desc[0] = h_desc[b]; h_n[0] = h_n[b]; have_prev = True
         return tot
     e2e_pass()
     barrier()
     t0 = time.perf_counter()
     for _ in range(args.e2e_steps):
-        tot = e2e_pass()
+        e2e_pass()
     barrier()
     t_e2e = time.perf_counter() - t0
     te = torch.tensor([t_e2e], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     e2e_value = world * ef * args.e2e_steps / float(te.item())
-    h2d = ef * fsz; d2h = ef * (kp_cap * 60 + 4)
+    h2d = ef * fsz + ef * kp_cap * 60 + ef * 4               # frames in; key points + descriptors + counts re-uploaded by the host matcher call
+    d2h = ef * (kp_cap * 60 + 4) + ef * (kp_cap * 4 + 4)     # key points, descriptors, counts; match indices, match counts
 
     sharded = None
     if world > 1 and not args.no_extra:
         import bench_extra
-        sharded = bench_extra.run_sharded_ba(local, rank, world, dist, torch)
+        sharded = bench_extra.run_multi(args, local, rank, world, dist, torch)
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
-    # ---- roofline of the dominant kernel (separate short pass with events between launches)
+    # ---- per-kernel roofline (separate short pass with events between launches)
     gb = geometry_bytes(cfg)
+    hbm, tf, how = peaks()
     fe.set_timing(True)
-    for c in range(0, min(frames, 4 * B), B):
+    nb = min(frames, 4 * B) // B
+    me0 = torch.cuda.Event(enable_timing=True); me1 = torch.cuda.Event(enable_timing=True); mms = 0.0
+    for c in range(0, nb * B, B):
         fe.run_dev(fish.data_ptr() + c * fsz, B, kps.data_ptr() + c * kp_cap * 28, desc.data_ptr() + c * kp_cap * 32, nout.data_ptr() + c * 4)
         fe.sync()
+        me0.record(ms)
+        mt.match_frames_dev(kps.data_ptr() + c * kp_cap * 28, desc.data_ptr() + c * kp_cap * 32, nout.data_ptr() + c * 4, kp_cap, B, match.data_ptr() + c * kp_cap * 4, nmatch.data_ptr() + c * 4)
+        me1.record(ms); mt.sync()
+        mms += me0.elapsed_time(me1)
     tm = fe.timing(); fe.set_timing(False)
+    tm["k_match_bruteforce"] = (mms, nb)
     total_ms = sum(v[0] for v in tm.values()) or 1.0
-    shares = {k: round(v[0] / total_ms, 4) for k, v in tm.items()}
-    algo = {"k_warp": gb["k_warp"], "k_pyramid": gb["k_pyramid"], "k_fast": gb["k_fast"],
-            "k_describe": int(nkp * (43 * 43 + 31 * 31 + 60)), "k_distribute": None}
-    dom = max(tm, key=lambda k: tm[k][0])
-    hbm, tf, how = peaks()
-    traffic = None
+    popc_peak = mt.ubench_popc()
+    algo = {"k_warp": gb["k_warp"], "k_pyramid": gb["k_pyramid"], "k_fast": gb["k_fast"], "k_describe": int(nkp * (43 * 43 + 31 * 31 + 60)), "k_distribute": None,
+            "k_match_bruteforce": int(2 * nkp * 36 + nkp * 8)}
+    traffic_tab = {}
     tp = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tp):
-        tj = json.load(open(tp))
-        if dom in tj.get("dram_bytes_per_frame", {}):
-            traffic = int(tj["dram_bytes_per_frame"][dom] * B)       # per launch group of one batch, like `achieved`
-    roof = {"kernel": dom, "bound": "hbm", "peak": hbm, "peak_source": how, "unit": "GB/s", "traffic": traffic, "share_of_step": shares[dom], "kernel_shares": shares}
+        traffic_tab = json.load(open(tp)).get("dram_bytes_per_frame", {})
+    per_kernel = {}
+    for k, (kms, _) in tm.items():
+        ent = {"share_of_step": round(kms / total_ms, 4), "ms_per_batch": round(kms / nb, 4)}
+        if algo.get(k):
+            ent["algorithmic_bytes_per_frame"] = algo[k]
+            ent["achieved_GBs"] = round(algo[k] * B / (kms / nb / 1e3) / 1e9, 2)
+            ent["frac_of_hbm"] = round(ent["achieved_GBs"] / hbm, 4)
+        if k == "k_match_bruteforce":
+            popc = (B - 1) * nkp * nkp * 8 / (kms / nb / 1e3)
+            ent.update({"bound": "popc issue", "achieved_popc32_per_s": round(popc, 3), "measured_peak_popc32_per_s": round(popc_peak, 3), "frac_of_popc_peak": round(popc / popc_peak, 4)})
+        per_kernel[k] = ent
+    dom = max(tm, key=lambda k: tm[k][0])
+    roof = {"kernel": dom, "bound": "hbm", "peak": hbm, "peak_source": how, "unit": "GB/s", "share_of_step": per_kernel[dom]["share_of_step"],
+            "achieved": per_kernel[dom].get("achieved_GBs"), "frac": per_kernel[dom].get("frac_of_hbm"),
+            "traffic": int(traffic_tab[dom] * B) if dom in traffic_tab else None, "per_kernel": per_kernel}
     if dom == "k_fast":
-        roof["note"] = ("k_fast is ALU-pipe bound, not HBM bound: the exact FAST arc score costs ~60 integer instructions per pixel "
-                        "(ncu: ALU pipe 68 % active, DRAM 2-3 %); `frac` is reported against HBM as the contract asks")
-    nbatches = min(frames, 4 * B) // B
-    if algo.get(dom):
-        # per launch: bytes of one batch; k_pyramid/k_fast are nlevels(-1) launches per batch -> use the per-batch total
-        per_batch_ms = tm[dom][0] / nbatches
-        roof["achieved"] = round(algo[dom] * B / (per_batch_ms / 1e3) / 1e9, 2)
-        roof["frac"] = round(roof["achieved"] / hbm, 4)
-        roof["algorithmic_bytes_per_frame"] = algo[dom]
-    else:
-        roof["achieved"] = None; roof["frac"] = None; roof["note"] = "latency-bound quadtree kernel; no HBM roofline applies"
-    whole = sum(v for v in [gb["k_warp"], gb["k_pyramid"], gb["k_fast"], 2 * gb["k_fast"], int(nkp * (43 * 43 + 31 * 31))])
-    roof["pipeline_algorithmic_bytes_per_frame"] = whole          # SURVEY §8d accounting (incl. the reference's whole-level blur)
+        roof["note"] = ("k_fast is integer-ALU bound, not HBM bound (ncu: ALU pipe ~68 % active, DRAM 2-3 %): `frac` is reported against HBM as the contract asks; "
+                        "see DESIGN.md §4 for the instruction-count argument")
+    whole = sum(v for v in [gb["k_warp"], gb["k_pyramid"], gb["k_fast"], 2 * gb["k_fast"], int(nkp * (43 * 43 + 31 * 31)), algo["k_match_bruteforce"]])
+    roof["pipeline_algorithmic_bytes_per_frame"] = whole          # SURVEY §8d accounting (incl. the reference's whole-level blur) + matcher I/O
     roof["pipeline_frac"] = round(whole * (value / world) / 1e9 / hbm, 4)
 
-    # ---- CPU baseline: the oracle port on the host cores, bounded sample of the same workload
     cpu = cpu_baseline(cfg, mask, base_host, args)
     extra = {}
     if sharded is not None:
-        extra = {"local_ba_sharded": sharded}
+        extra = sharded
     elif not args.no_extra:
         import bench_extra
-        fe.close()
-        del fish, kps, desc
+        fe.close(); mt.close()
+        del fish, kps, desc, match
         torch.cuda.empty_cache()
         extra = bench_extra.run(args, local)
-    out = {"metric": "warp+ORB-extract frames/sec", "value": round(value, 1), "unit": "frames/s", "n_gpus": world, "steps": args.steps,
+    out = {"metric": METRIC, "value": round(value, 1), "unit": "frames/s", "n_gpus": world, "steps": args.steps,
            "warmup": args.warmup, "ms_per_step": round(ms_max / args.steps, 3), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
            "dtype": "u8", "data": "synthetic (SURVEY §8d recipe: %d distinct frames, others are re-masked circular shifts)" % N_BASE,
-           "config": {"workload": "configs[1]: warp + ORB extract, %d synthetic 1280x1024 frames per GPU, 650-px faces, nFeatures 3000" % frames,
+           "config": {"workload": "configs[1]+[2]: warp + ORB extract of %d synthetic 1280x1024 frames per GPU (650-px faces, nFeatures 3000) + all-pairs Hamming match of consecutive frames" % frames,
                       "frames_per_gpu": frames, "batch": B, "l2": "inputs (%.1f GB) larger than L2" % (frames * fsz / 1e9), "parallelism": "frame-shard x%d" % world,
-                      "mean_keypoints_per_frame": round(nkp, 1)},
+                      "mean_keypoints_per_frame": round(nkp, 1), "mean_matches_per_pair": round(nmt, 1),
+                      "second_metric": "LocalBA LM iterations/s: extra.local_ba.lm_iters_per_s"},
            "clocks": clocks, "gpu_launches": int(launches),
            "e2e": {"value": round(e2e_value, 1), "unit": "frames/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                   "frames_per_step": ef, "steps": args.e2e_steps},
+                   "frames_per_step": ef, "steps": args.e2e_steps, "calls": "cslam_frontend_run + cslam_match_frames (host buffers)"},
            "roofline": roof, "cpu_baseline": cpu, "extra": extra}
     print(json.dumps(out))
     if world > 1:
@@ -288,21 +311,88 @@ def host_cores():
     return n
 
 
-def cpu_baseline(cfg, mask, base_frames, args, threads=None, nframes=None):
+def cv2_primitive_ms(cfg):
+    """opencv-python 4.13 wall time of the bare OpenCV primitives on one 1950^2 canvas, 1 thread: a sanity lower bound for any CPU path."""
+    try:
+        import cv2
+    except Exception:
+        return None
+    cv2.setNumThreads(1)
+    rng = np.random.default_rng(0)
+    W3 = 3 * int(cfg["CubeFace.w"])
+    img = cv2.resize(rng.integers(0, 256, (W3 // 8, W3 // 8), dtype=np.uint8), (W3, W3))
+    out = {}
+    t0 = time.perf_counter(); lv = [img]
+    for l in range(1, 8):
+        s = int(round(W3 / 1.2 ** l)); lv.append(cv2.resize(lv[-1], (s, s), interpolation=cv2.INTER_LINEAR))
+    out["pyramid_ms"] = round(1e3 * (time.perf_counter() - t0), 2)
+    t0 = time.perf_counter()
+    for a in lv:
+        cv2.GaussianBlur(a, (7, 7), 2, 2, borderType=cv2.BORDER_REFLECT_101)
+    out["blur_ms"] = round(1e3 * (time.perf_counter() - t0), 2)
+    fd = cv2.FastFeatureDetector_create(20, True, cv2.FAST_FEATURE_DETECTOR_TYPE_9_16)
+    t0 = time.perf_counter()
+    for a in lv:
+        fd.detect(a)
+    out["fast_whole_image_ms"] = round(1e3 * (time.perf_counter() - t0), 2)
+    m = rng.uniform(0, 1000, (int(cfg["CubeFace.w"]), int(cfg["CubeFace.w"]))).astype(np.float32)
+    src = rng.integers(0, 256, (int(cfg["Camera.Ih"]), int(cfg["Camera.Iw"])), dtype=np.uint8)
+    t0 = time.perf_counter()
+    for _ in range(5):
+        cv2.remap(src, m, m, cv2.INTER_LINEAR)
+    out["remap_5_faces_ms"] = round(1e3 * (time.perf_counter() - t0), 2)
+    out["threads"] = 1
+    return out
+
+
+def cpu_baseline(cfg, mask, base_frames, args, threads=None, nframes=None, with_cv2=True):
+    """Warp + extract + consecutive-frame matching on the host cores, bounded sample. Extraction runs the reference's OWN ORBExtractor.cpp /
+    CamModelGeneral.cpp (oracle/_ref/libref.so, compiled unmodified against the cv:: shim) when that library travelled with the tree, else the
+    oracle port; the all-pairs matcher has no reference function and is the oracle port in both cases."""
     import oracle as orc
     quota = host_cores()
     cores = threads or min(os.cpu_count() or 1, 2 * quota)     # 2 worker threads per granted CPU measured fastest on the box
     cp = orc.cam_params(cfg)
     m1, m2 = orc.build_maps(cp)
-    n = nframes or 20 * cores          # ~10 s of CPU work at the measured rate
+    n = nframes or 16 * cores
     fr = np.stack([base_frames[i % len(base_frames)] for i in range(n)])
-    orc.warp_extract_batch(cp, fr[:min(n, cores)], m1, m2, mask, 3000, 1.2, 8, 20, 7, cores)     # warm-up
+    cap = 3000 + 24
+    kind = "port"
+    try:
+        from oracle import ref as R
+        if R.available():
+            kind = "reference"
+    except Exception:
+        pass
+    if kind == "reference":
+        r = R.Ref(cp)
+        r.warp_extract_batch_out(fr[:min(n, cores)], m1, m2, mask, 3000, 1.2, 8, 20, 7, cores, cap)     # warm-up
+        t0 = time.perf_counter()
+        kps, desc, nn = r.warp_extract_batch_out(fr, m1, m2, mask, 3000, 1.2, 8, 20, 7, cores, cap)
+        t_ext = time.perf_counter() - t0
+        t0 = time.perf_counter()
+        r.warp_extract_batch_out(fr[:max(4, n // 8)], m1, m2, mask, 3000, 1.2, 8, 20, 7, 1, cap)
+        t_one = (time.perf_counter() - t0) / max(4, n // 8)
+    else:
+        orc.warp_extract_batch_out(cp, fr[:min(n, cores)], m1, m2, mask, 3000, 1.2, 8, 20, 7, cores, cap)
+        t0 = time.perf_counter()
+        kps, desc, nn = orc.warp_extract_batch_out(cp, fr, m1, m2, mask, 3000, 1.2, 8, 20, 7, cores, cap)
+        t_ext = time.perf_counter() - t0
+        t0 = time.perf_counter()
+        orc.warp_extract_batch_out(cp, fr[:max(4, n // 8)], m1, m2, mask, 3000, 1.2, 8, 20, 7, 1, cap)
+        t_one = (time.perf_counter() - t0) / max(4, n // 8)
     t0 = time.perf_counter()
-    tot = orc.warp_extract_batch(cp, fr, m1, m2, mask, 3000, 1.2, 8, 20, 7, cores)
-    dt = time.perf_counter() - t0
-    return {"value": round(n / dt, 2), "unit": "frames/s", "cores": quota, "threads": cores, "kind": "port",
-            "sample": "%d frames of the same workload, %d independent worker threads on %d granted CPUs (C++ oracle, -O3)" % (n, cores, quota), "seconds": round(dt, 2),
-            "mean_keypoints_per_frame": round(tot / n, 1)}
+    nm, _ = orc.match_frames_batch(kps, desc, nn, 0.6, 50, True, nthreads=cores)
+    t_match = time.perf_counter() - t0
+    dt = t_ext + t_match
+    out = {"value": round(n / dt, 2), "unit": "frames/s", "cores": quota, "threads": cores, "kind": kind,
+           "sample": "%d frames of the same workload, %d independent worker threads on %d granted CPUs; extraction = %s, matching = oracle port (-O3)"
+                     % (n, cores, quota, "the reference's ORBExtractor.cpp compiled unmodified (oracle/_ref)" if kind == "reference" else "oracle port"),
+           "seconds": round(dt, 2), "extract_frames_per_s": round(n / t_ext, 2), "match_pairs_per_s": round((n - 1) / max(t_match, 1e-9), 2),
+           "single_thread_extract_frames_per_s": round(1.0 / t_one, 2), "mean_keypoints_per_frame": round(float(nn.mean()), 1), "mean_matches_per_pair": round(float(nm[:n - 1].mean()), 1)}
+    if with_cv2:
+        out["cv2_primitives_1_thread"] = cv2_primitive_ms(cfg)
+    return out
 
 
 def run_reference(args):
@@ -314,14 +404,14 @@ def run_reference(args):
     base = np.stack([synth.fisheye_frame(cfg, i) for i in range(N_BASE)])
     vals = []
     for i in range(args.warmup + args.steps):
-        c = cpu_baseline(cfg, mask, base, args, nframes=256)
+        c = cpu_baseline(cfg, mask, base, args, nframes=192, with_cv2=(i == args.warmup + args.steps - 1))
         if i >= args.warmup:
             vals.append(c)
     v = float(np.mean([c["value"] for c in vals]))
     c = vals[-1]; c["value"] = round(v, 2)
-    out = {"impl": "reference", "metric": "warp+ORB-extract frames/sec", "value": round(v, 2), "unit": "frames/s", "n_gpus": args.gpus, "steps": args.steps,
+    out = {"impl": "reference", "metric": METRIC, "value": round(v, 2), "unit": "frames/s", "n_gpus": args.gpus, "steps": args.steps,
            "warmup": args.warmup, "ms_per_step": round(1e3 * c["seconds"], 1), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8",
-           "data": "synthetic", "config": {"workload": "configs[1]: warp + ORB extract, 1280x1024 frames, 650-px faces, nFeatures 3000 (bounded sample per step)"},
+           "data": "synthetic", "config": {"workload": "configs[1]+[2]: warp + ORB extract + consecutive-frame match, 1280x1024 frames, 650-px faces, nFeatures 3000 (bounded sample of 192 frames per step)"},
            "cpu_baseline": c, "e2e": {"value": round(v, 2), "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(out))
 
@@ -339,6 +429,7 @@ def main():
     ap.add_argument("--match-pairs", type=int, default=4096)
     ap.add_argument("--match-steps", type=int, default=2)
     ap.add_argument("--pose-frames", type=int, default=2048)
+    ap.add_argument("--track-frames", type=int, default=1024)
     ap.add_argument("--no-extra", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -258,6 +258,7 @@ struct cslam_matcher {
     uint8_t *dA = nullptr, *dB = nullptr, *dValid = nullptr;
     float *aA = nullptr, *aB = nullptr;
     int32_t *nodeA = nullptr, *nodeB = nullptr, *dMatch = nullptr, *dDist = nullptr, *dSecond = nullptr, *dN = nullptr;
+    cslam_keypoint* dKps = nullptr;   // staging of cslam_match_frames (lazily allocated)
     int64_t launches = 0;
 };
 
@@ -287,7 +288,7 @@ extern "C" void cslam_matcher_destroy(cslam_matcher* m) {
     if (!m) return;
     cudaSetDevice(m->device);
     if (m->stream) { cudaStreamSynchronize(m->stream); cudaStreamDestroy(m->stream); }
-    void* ptrs[] = {m->dA, m->dB, m->dValid, m->aA, m->aB, m->nodeA, m->nodeB, m->dMatch, m->dDist, m->dSecond, m->dN};
+    void* ptrs[] = {m->dA, m->dB, m->dValid, m->aA, m->aB, m->nodeA, m->nodeB, m->dMatch, m->dDist, m->dSecond, m->dN, m->dKps};
     for (void* p : ptrs) if (p) cudaFree(p);
     delete m;
 }
@@ -353,6 +354,24 @@ extern "C" int cslam_match_frames_dev(cslam_matcher* m, const cslam_keypoint* kp
                                                                    match12, nullptr, nullptr, nmatches, L);
     m->launches++;
     CSLAM_CUDA(cudaGetLastError());
+    return CSLAM_OK;
+}
+
+// host buffers in / out (copies inside, synchronous): kps / desc / n as cslam_frontend_run returns them
+extern "C" int cslam_match_frames(cslam_matcher* m, const cslam_keypoint* kps, const uint8_t* desc, const int32_t* n, int kp_stride, int nframes, float nnratio, int th_low,
+                                  int check_ori, int32_t* match12, int32_t* nmatches) {
+    if (!m || nframes < 2 || nframes > m->maxPairs || kp_stride <= 0 || kp_stride > m->maxFeat) { set_error("cslam_match_frames: sizes out of range (frames %d/%d, stride %d/%d)", nframes, m ? m->maxPairs : 0, kp_stride, m ? m->maxFeat : 0); return CSLAM_E_BADARG; }
+    CSLAM_CUDA(cudaSetDevice(m->device));
+    const size_t nf = (size_t)nframes * kp_stride;
+    if (!m->dKps) CSLAM_CUDA(cudaMalloc(&m->dKps, (size_t)m->maxPairs * m->maxFeat * sizeof(cslam_keypoint)));
+    CSLAM_CUDA(cudaMemcpyAsync(m->dKps, kps, nf * sizeof(cslam_keypoint), cudaMemcpyHostToDevice, m->stream));
+    CSLAM_CUDA(cudaMemcpyAsync(m->dA, desc, nf * 32, cudaMemcpyHostToDevice, m->stream));
+    CSLAM_CUDA(cudaMemcpyAsync(m->nodeA, n, (size_t)nframes * 4, cudaMemcpyHostToDevice, m->stream));
+    int rc = cslam_match_frames_dev(m, m->dKps, m->dA, m->nodeA, kp_stride, nframes, nnratio, th_low, check_ori, m->dMatch, m->dN);
+    if (rc) return rc;
+    CSLAM_CUDA(cudaMemcpyAsync(match12, m->dMatch, (size_t)(nframes - 1) * kp_stride * 4, cudaMemcpyDeviceToHost, m->stream));
+    CSLAM_CUDA(cudaMemcpyAsync(nmatches, m->dN, (size_t)(nframes - 1) * 4, cudaMemcpyDeviceToHost, m->stream));
+    CSLAM_CUDA(cudaStreamSynchronize(m->stream));
     return CSLAM_OK;
 }
 

@@ -13,6 +13,7 @@ namespace cslam {
 struct PoseOptArgs {
     const int* offset; float* Tcw; const float* Xw; const float* kpxy; const float* invSigma2;
     int faceW, faceH; uint8_t* outlier; int32_t* inliers; double* pose64; double* err; uint8_t* level;
+    const int32_t* count; int stride;   // offset == nullptr: frame f owns correspondences [f*stride, f*stride + count[f])
 };
 
 // The kernel is a long sequential schedule of block-wide phases. Every phase is an out-of-line device function (all threads call it
@@ -142,7 +143,7 @@ __global__ void __launch_bounds__(256) k_pose_opt(PoseOptArgs A) {
     const int f = blockIdx.x, tid = threadIdx.x, T = blockDim.x;
     PoFrame F;
     F.Xw = A.Xw; F.kpxy = A.kpxy; F.invSigma2 = A.invSigma2; F.err = A.err; F.level = A.level; F.outlier = A.outlier;
-    F.beg = A.offset[f]; F.n = A.offset[f + 1] - F.beg; F.faceW = A.faceW; F.faceH = A.faceH; F.fc = A.faceW / 2.0;
+    if (A.offset) { F.beg = A.offset[f]; F.n = A.offset[f + 1] - F.beg; } else { F.beg = f * A.stride; F.n = min(A.count[f], A.stride); } F.faceW = A.faceW; F.faceH = A.faceH; F.fc = A.faceW / 2.0;
     const float dlt = (float)sqrt(5.991); F.delta = (double)dlt; F.dsqr = F.delta * F.delta;
     const int beg = F.beg, n = F.n;
     if (tid == 0) { S.pose0 = pose_from_Tcw32(A.Tcw + 16 * f); S.pose = S.pose0; }
@@ -244,5 +245,30 @@ extern "C" int cslam_pose_optimization(cslam_optimizer* o, int nframes, const in
     CSLAM_CUDA(cudaStreamSynchronize(o->stream));
     for (int f = 0; f < nframes; f++) if (offset[f + 1] - offset[f] >= 3) std::memcpy(Tcw + 16 * f, Tout.data() + 16 * f, 64);
     free_pool(o);
+    return CSLAM_OK;
+}
+
+// Device-resident variant for pipelines (config 5): fixed stride, per-frame counts, all pointers on the device, asynchronous on the optimizer's stream.
+extern "C" int cslam_pose_optimization_dev(cslam_optimizer* o, int nframes, int stride, const int32_t* count, float* Tcw, const float* Xw, const float* kp_xy, const float* inv_sigma2,
+                                           int face_w, int face_h, uint8_t* outlier, int32_t* inliers) {
+    if (!o || nframes <= 0 || stride <= 0 || !count || !Tcw || !Xw || !kp_xy || !inv_sigma2 || !outlier || !inliers) { set_error("cslam_pose_optimization_dev: bad argument"); return CSLAM_E_BADARG; }
+    if (face_w != face_h || face_w <= 0) { set_error("cube faces must be square"); return CSLAM_E_BADARG; }
+    CSLAM_CUDA(cudaSetDevice(o->device));
+    free_pool(o);
+    PoseOptArgs A; std::memset(&A, 0, sizeof(A));
+    double* d_err; uint8_t* d_lvl; int rc;
+    const size_t n = (size_t)nframes * stride;
+    if ((rc = dalloc(o, &d_err, n * 2)) || (rc = dalloc(o, &d_lvl, n))) return rc;
+    A.offset = nullptr; A.count = count; A.stride = stride; A.Tcw = Tcw; A.Xw = Xw; A.kpxy = kp_xy; A.invSigma2 = inv_sigma2; A.faceW = face_w; A.faceH = face_h;
+    A.outlier = outlier; A.inliers = inliers; A.pose64 = nullptr; A.err = d_err; A.level = d_lvl;
+    k_pose_opt<<<nframes, 256, 0, o->stream>>>(A); o->launches++;
+    CSLAM_CUDA(cudaGetLastError());
+    return CSLAM_OK;
+}
+extern "C" void* cslam_optimizer_stream(const cslam_optimizer* o) { return o ? (void*)o->stream : nullptr; }
+extern "C" int cslam_optimizer_sync(cslam_optimizer* o) {
+    if (!o) return CSLAM_E_BADARG;
+    CSLAM_CUDA(cudaSetDevice(o->device));
+    CSLAM_CUDA(cudaStreamSynchronize(o->stream));
     return CSLAM_OK;
 }

@@ -316,9 +316,46 @@ __global__ void __launch_bounds__(TRK_WARPS * 32) k_search_by_projection(TrackAr
     if (tid == 0) A.nmatches[p] = total;
 }
 
+// What Tracking does between SearchByProjection and PoseOptimization (src/Optimizer.cpp:80-131 reads mvpMapPoints / mvKeys / mvKeyRays):
+// the matched slots of a frame, in slot order, become the (world point, key point, 1/sigma^2) correspondences of the pose-only BA.
+__global__ void __launch_bounds__(256) k_gather_pose_inputs(const int32_t* __restrict__ match, const cslam_keypoint* __restrict__ kCur, const int32_t* __restrict__ nCur, int curStride,
+                                                            const float* __restrict__ rays, float cosFovTh, const float* __restrict__ XwLast, int lastStride, const float* invSigma2,
+                                                            float* __restrict__ XwOut, float* __restrict__ kpOut, float* __restrict__ wOut, int32_t* __restrict__ count) {
+    __shared__ int wcnt[8], base;
+    const int p = blockIdx.x, tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    const int n = min(nCur[p], curStride);
+    if (tid == 0) base = 0;
+    __syncthreads();
+    for (int i0 = 0; i0 < n; i0 += 256) {
+        const int i = i0 + tid;
+        int m = -1;
+        if (i < n) { m = match[(size_t)p * curStride + i]; if (m >= 0 && rays && rays[((size_t)p * curStride + i) * 3 + 2] < cosFovTh) m = -1; }
+        const unsigned ball = __ballot_sync(0xffffffffu, m >= 0);
+        if (lane == 0) wcnt[w] = __popc(ball);
+        __syncthreads();
+        int pre = base;
+        for (int ww = 0; ww < w; ww++) pre += wcnt[ww];
+        if (m >= 0) {
+            const size_t o = (size_t)p * curStride + pre + __popc(ball & ((1u << lane) - 1));
+            const cslam_keypoint kp = kCur[(size_t)p * curStride + i];
+            const float* X = XwLast + ((size_t)p * lastStride + m) * 3;
+            XwOut[3 * o] = X[0]; XwOut[3 * o + 1] = X[1]; XwOut[3 * o + 2] = X[2];
+            kpOut[2 * o] = kp.x; kpOut[2 * o + 1] = kp.y; wOut[o] = invSigma2[kp.octave];
+        }
+        __syncthreads();
+        if (tid == 0) { int t = 0; for (int ww = 0; ww < 8; ww++) t += wcnt[ww]; base += t; }
+        __syncthreads();
+    }
+    if (tid == 0) count[p] = base;
+}
+
 }  // namespace cslam
 
 using namespace cslam;
+
+extern "C" int cslam_tracker_gather_pose_inputs_dev(cslam_tracker* t, int npairs, const int32_t* match_cur, const cslam_keypoint* k_cur, const int32_t* n_cur, int cur_stride,
+                                                    const float* rays_cur, float cos_fov_th, const float* Xw_last, int last_stride, const float* inv_sigma2_levels_dev,
+                                                    float* Xw_out, float* kp_xy_out, float* inv_sigma2_out, int32_t* count_out);
 
 // ---- host utility (no device needed): the cell rectangles Frame::GetFeaturesInArea visits, for callers that keep the grid on the host
 extern "C" int cslam_area_rects(float x, float y, float r, int face_w, int face_h, int32_t* rects /* 3 x 5: face, x0, x1, y0, y1 (unclamped) */) {
@@ -386,6 +423,18 @@ extern "C" int cslam_tracker_sync(cslam_tracker* t) {
     CSLAM_CUDA(cudaMemcpyAsync(&e, t->err, sizeof(int), cudaMemcpyDeviceToHost, t->stream));
     CSLAM_CUDA(cudaStreamSynchronize(t->stream));
     if (e) { cudaMemsetAsync(t->err, 0, sizeof(int), t->stream); set_error("tracker: a search window held more candidates than the fixed capacity"); return e; }
+    return CSLAM_OK;
+}
+
+extern "C" int cslam_tracker_gather_pose_inputs_dev(cslam_tracker* t, int npairs, const int32_t* match_cur, const cslam_keypoint* k_cur, const int32_t* n_cur, int cur_stride,
+                                                    const float* rays_cur, float cos_fov_th, const float* Xw_last, int last_stride, const float* inv_sigma2_levels_dev,
+                                                    float* Xw_out, float* kp_xy_out, float* inv_sigma2_out, int32_t* count_out) {
+    if (!t || npairs <= 0 || !match_cur || !k_cur || !n_cur || !Xw_last || !inv_sigma2_levels_dev || !Xw_out || !kp_xy_out || !inv_sigma2_out || !count_out) { set_error("cslam_tracker_gather_pose_inputs_dev: bad argument"); return CSLAM_E_BADARG; }
+    CSLAM_CUDA(cudaSetDevice(t->device));
+    k_gather_pose_inputs<<<npairs, 256, 0, t->stream>>>(match_cur, k_cur, n_cur, cur_stride, rays_cur, cos_fov_th, Xw_last, last_stride, inv_sigma2_levels_dev, Xw_out, kp_xy_out,
+                                                       inv_sigma2_out, count_out);
+    t->launches++;
+    CSLAM_CUDA(cudaGetLastError());
     return CSLAM_OK;
 }
 

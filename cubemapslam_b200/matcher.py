@@ -76,6 +76,13 @@ class ORBMatcher:
         check(lib().cslam_match_frames_dev(self._h, ptr(kps), ptr(desc), ptr(n), int(kp_stride), int(nframes), C.c_float(self.nnratio), int(th_low), int(self.check_ori),
                                            ptr(match12), ptr(nmatches)))
 
+    def match_frames(self, kps, desc, n, th_low=TH_LOW):
+        """Host arrays as FrontEnd.run_raw fills them: kps (F, stride) records, desc (F, stride, 32), n (F,). Returns nmatches (F-1,), match12 (F-1, stride)."""
+        F, stride = kps.shape[0], kps.shape[1]
+        match = np.empty((F - 1, stride), np.int32); nm = np.empty(F - 1, np.int32)
+        check(lib().cslam_match_frames(self._h, ptr(kps), ptr(desc), ptr(n), int(stride), int(F), C.c_float(self.nnratio), int(th_low), int(self.check_ori), ptr(match), ptr(nm)))
+        return nm, match
+
     def ubench_popc(self):
         v = C.c_double()
         check(lib().cslam_ubench_popc(self._h, C.byref(v)))

@@ -54,6 +54,18 @@ class Optimizer:
         return dict(Tcw=Tcw.reshape(nKF, 4, 4), pts=pts, outlier=outlier[:nE], pose64=pose64, pts64=pts64[:nMP], log=log[:r.iterations], iters=r.iterations,
                     trials=r.trials)
 
+    @property
+    def stream(self):
+        lib().cslam_optimizer_stream.restype = C.c_void_p
+        return lib().cslam_optimizer_stream(self._h)
+
+    def sync(self):
+        check(lib().cslam_optimizer_sync(self._h))
+
+    def pose_optimization_dev(self, nframes, stride, count, Tcw, Xw, kpxy, inv_sigma2, faceW, faceH, outlier, inliers):
+        check(lib().cslam_pose_optimization_dev(self._h, int(nframes), int(stride), ptr(count), ptr(Tcw), ptr(Xw), ptr(kpxy), ptr(inv_sigma2), int(faceW), int(faceH), ptr(outlier),
+                                                ptr(inliers)))
+
     def PoseOptimization(self, Tcw, Xw, kpxy, inv_sigma2, faceW, faceH, offset=None):
         """Single frame (Tcw 4x4, Xw n x 3, ...) or a batch (Tcw F x 4 x 4, offset F+1 into the concatenated correspondences)."""
         Tcw = np.ascontiguousarray(Tcw, np.float32)

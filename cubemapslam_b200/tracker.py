@@ -97,3 +97,13 @@ class Tracker:
         check(lib().cslam_search_by_projection_local(self._h, P, ptr(k), ptr(a[0]), ptr(nf), fs, ptr(a[7]), ptr(nm_), ms, ptr(a[1]), ptr(a[2]), ptr(a[3]), ptr(a[4]), ptr(a[5]), ptr(a[6]),
                                                      int(face_w), int(face_h), C.c_float(th), C.c_float(nnratio), C.c_float(scale_factor), int(nlevels), ptr(match), ptr(nm)))
         return (int(nm[0]), match[0]) if single else (nm, match)
+
+    def search_by_projection_last_dev(self, npairs, kCur, dCur, nCur, cur_stride, cell_start, cell_idx, curTaken, TcwCur, kLast, nLast, last_stride, hasMP, Xw, dMP, mpObs,
+                                      face_w, face_h, cos_fov_th, th, check_ori, match, nmatches, scale_factor=1.2, nlevels=8):
+        check(lib().cslam_search_by_projection_last_dev(self._h, int(npairs), ptr(kCur), ptr(dCur), ptr(nCur), int(cur_stride), ptr(cell_start), ptr(cell_idx), ptr(curTaken), ptr(TcwCur),
+                                                        ptr(kLast), ptr(nLast), int(last_stride), ptr(hasMP), ptr(Xw), ptr(dMP), ptr(mpObs), int(face_w), int(face_h),
+                                                        C.c_float(cos_fov_th), C.c_float(th), int(check_ori), C.c_float(scale_factor), int(nlevels), ptr(match), ptr(nmatches)))
+
+    def gather_pose_inputs_dev(self, npairs, match, kCur, nCur, cur_stride, rays, cos_fov_th, XwLast, last_stride, inv_sigma2_levels, XwOut, kpOut, wOut, count):
+        check(lib().cslam_tracker_gather_pose_inputs_dev(self._h, int(npairs), ptr(match), ptr(kCur), ptr(nCur), int(cur_stride), ptr(rays), C.c_float(cos_fov_th), ptr(XwLast),
+                                                         int(last_stride), ptr(inv_sigma2_levels), ptr(XwOut), ptr(kpOut), ptr(wOut), ptr(count)))

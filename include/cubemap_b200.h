@@ -116,6 +116,8 @@ int cslam_match_bruteforce_dev(cslam_matcher* m, const uint8_t* descA, const flo
  * asynchronous): frame f is matched against frame f+1, f = 0 .. nframes-2; kp_stride = cslam_frontend_kp_capacity; n = the front end's n_out. */
 int cslam_match_frames_dev(cslam_matcher* m, const cslam_keypoint* kps, const uint8_t* desc, const int32_t* n, int kp_stride, int nframes, float nnratio, int th_low,
                            int check_ori, int32_t* match12, int32_t* nmatches);
+int cslam_match_frames(cslam_matcher* m, const cslam_keypoint* kps, const uint8_t* desc, const int32_t* n, int kp_stride, int nframes, float nnratio, int th_low, int check_ori,
+                       int32_t* match12, int32_t* nmatches);   /* host buffers, synchronous */
 /* Measured POPC issue rate of this GPU (32-bit population counts per second with the XOR+POPC+ADD mix of the Hamming kernels, no memory traffic):
  * the ceiling the matcher's roofline fraction is quoted against (bench.py). */
 int cslam_ubench_popc(cslam_matcher* m, double* popc32_per_s);
@@ -183,6 +185,13 @@ int cslam_search_by_projection_local_dev(cslam_tracker* t, int nframes, const cs
                                          const uint8_t* mp_obs, int face_w, int face_h, float th, float nnratio, float scale_factor, int nlevels, int32_t* match_f,
                                          int32_t* nmatches);
 
+/* What Tracking does between SearchByProjection and PoseOptimization (src/Optimizer.cpp:80-131): the matched slots of each frame, in slot order and
+ * with the ray.z >= cos_fov_th test when rays are given, become (world point, key point, 1/sigma^2) correspondences at stride cur_stride; count_out[p] of them.
+ * inv_sigma2_levels_dev: mvInvLevelSigma2 (one float per pyramid level) on the device. Device pointers, asynchronous on the tracker's stream. */
+int cslam_tracker_gather_pose_inputs_dev(cslam_tracker* t, int npairs, const int32_t* match_cur, const cslam_keypoint* k_cur, const int32_t* n_cur, int cur_stride,
+                                         const float* rays_cur, float cos_fov_th, const float* Xw_last, int last_stride, const float* inv_sigma2_levels_dev,
+                                         float* Xw_out, float* kp_xy_out, float* inv_sigma2_out, int32_t* count_out);
+
 /* ---------------------------------------------------------------------------------------------- optimizer
  * Optimizer::LocalBundleAdjustment (src/Optimizer.cpp:192-451) on the already collected local window.
  * Vertices must be ordered like g2o orders them: KFs by mnId, points by mnId. */
@@ -225,6 +234,13 @@ int cslam_local_ba(cslam_optimizer* o, cslam_ba_problem* p, const volatile uint8
 int cslam_pose_optimization(cslam_optimizer* o, int nframes, const int32_t* offset, float* Tcw, const float* Xw,
                             const float* kp_xy, const float* inv_sigma2, int face_w, int face_h, uint8_t* outlier,
                             int32_t* inliers, double* pose_fp64);
+
+/* Device-resident PoseOptimization for pipelines: frame f owns correspondences [f*stride, f*stride + count[f]); all pointers on the device;
+ * asynchronous on the optimizer's stream (cslam_optimizer_stream / cslam_optimizer_sync). */
+int cslam_pose_optimization_dev(cslam_optimizer* o, int nframes, int stride, const int32_t* count, float* Tcw, const float* Xw, const float* kp_xy, const float* inv_sigma2,
+                                int face_w, int face_h, uint8_t* outlier, int32_t* inliers);
+void* cslam_optimizer_stream(const cslam_optimizer* o);
+int cslam_optimizer_sync(cslam_optimizer* o);
 
 #ifdef __cplusplus
 }

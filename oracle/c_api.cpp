@@ -117,6 +117,51 @@ void orc_match_bruteforce_batch(const uint8_t* descA, const float* angA, int nA,
     for (auto& x : th) x.join();
 }
 
+// all-pairs matching of consecutive frames (frame f vs f+1) in the front end's output layout, `nthreads` workers; returns total matches
+long orc_match_frames_batch(const KeyPoint* kps, const uint8_t* desc, const int* n, int stride, int nframes, float nnratio, int thLow, int checkOri, int* match12, int* nmatches,
+                            int nthreads) {
+    std::vector<long> totals(nthreads, 0);
+    auto work = [&](int t) {
+        std::vector<float> aA(stride), aB(stride); std::vector<int> d(stride), s2(stride);
+        for (int f = t; f + 1 < nframes; f += nthreads) {
+            const int nA = n[f], nB = n[f + 1];
+            for (int i = 0; i < nA; i++) aA[i] = kps[(size_t)f * stride + i].angle;
+            for (int i = 0; i < nB; i++) aB[i] = kps[(size_t)(f + 1) * stride + i].angle;
+            nmatches[f] = match_bruteforce(desc + (size_t)f * stride * 32, aA.data(), nA, desc + (size_t)(f + 1) * stride * 32, aB.data(), nB, nnratio, thLow, checkOri != 0,
+                                           match12 + (size_t)f * stride, d.data(), s2.data());
+            totals[t] += nmatches[f];
+        }
+    };
+    std::vector<std::thread> th;
+    for (int t = 1; t < nthreads; t++) th.emplace_back(work, t);
+    work(0);
+    for (auto& x : th) x.join();
+    long s = 0; for (long v : totals) s += v; return s;
+}
+// warp + extract with per-frame outputs (for the extract+match CPU baseline): kps / desc: nframes x cap
+long orc_warp_extract_batch_out(const CamParams* cp, const uint8_t* fisheyes, int nframes, const float* map1, const float* map2, const uint8_t* mask, int nfeatures, float scaleFactor,
+                                int nlevels, int iniTh, int minTh, int nthreads, int cap, KeyPoint* kpsOut, uint8_t* descOut, int* nOut) {
+    std::vector<long> totals(nthreads, 0);
+    auto work = [&](int t) {
+        ORBextractor ex(nfeatures, scaleFactor, nlevels, iniTh, minTh, cp->faceW, cp->faceH);
+        const int W3 = 3 * cp->faceW, H3 = 3 * cp->faceH;
+        std::vector<uint8_t> canvas((size_t)W3 * H3, 0), desc; std::vector<KeyPoint> kps;
+        for (int f = t; f < nframes; f += nthreads) {
+            warp_fisheye_to_cubemap(*cp, fisheyes + (size_t)f * cp->Iw * cp->Ih, cp->Iw, map1, map2, canvas.data(), W3);
+            ex(canvas.data(), W3, H3, W3, mask, W3, kps, desc);
+            const int m = std::min((int)kps.size(), cap);
+            nOut[f] = m;
+            if (m) { std::memcpy(kpsOut + (size_t)f * cap, kps.data(), (size_t)m * sizeof(KeyPoint)); std::memcpy(descOut + (size_t)f * cap * 32, desc.data(), (size_t)m * 32); }
+            totals[t] += m;
+        }
+    };
+    std::vector<std::thread> th;
+    for (int t = 1; t < nthreads; t++) th.emplace_back(work, t);
+    work(0);
+    for (auto& x : th) x.join();
+    long s = 0; for (long v : totals) s += v; return s;
+}
+
 // ---- per-frame indexing (rays, 5x50x50 grid) and windowed lookup
 void orc_key_point_rays(const KeyPoint* kps, int n, int faceW, int faceH, float* rays, int* faces) {
     for (int i = 0; i < n; i++) { const int f = fi_pixel_to_ray(kps[i].x, kps[i].y, faceW, faceH, rays + 3 * i); if (faces) faces[i] = f; }

@@ -177,6 +177,24 @@ def warp_extract_batch(cp, fisheyes, m1, m2, mask, nfeatures, scaleFactor, nleve
                                         C.c_float(scaleFactor), int(nlevels), int(iniTh), int(minTh), int(nthreads))
 
 
+def warp_extract_batch_out(cp, fisheyes, m1, m2, mask, nfeatures, scaleFactor, nlevels, iniTh, minTh, nthreads, cap):
+    fisheyes = _u8(fisheyes); mask = _u8(mask); F = fisheyes.shape[0]
+    kps = np.zeros((F, cap), KP_DTYPE); desc = np.zeros((F, cap, 32), np.uint8); n = np.zeros(F, np.int32)
+    lib().orc_warp_extract_batch_out.restype = C.c_long
+    lib().orc_warp_extract_batch_out(C.byref(cp), _p(fisheyes), F, _p(m1), _p(m2), _p(mask), int(nfeatures), C.c_float(scaleFactor), int(nlevels), int(iniTh), int(minTh),
+                                     int(nthreads), int(cap), _p(kps), _p(desc), _p(n))
+    return kps, desc, n
+
+
+def match_frames_batch(kps, desc, n, nnratio=0.6, thLow=50, checkOri=True, nthreads=1):
+    kps = np.ascontiguousarray(kps); desc = _u8(desc); n = _i32(n)
+    F, stride = kps.shape
+    m = np.full((max(F - 1, 1), stride), -1, np.int32); nm = np.zeros(max(F - 1, 1), np.int32)
+    lib().orc_match_frames_batch.restype = C.c_long
+    lib().orc_match_frames_batch(_p(kps), _p(desc), _p(n), stride, F, C.c_float(nnratio), int(thLow), int(checkOri), _p(m), _p(nm), int(nthreads))
+    return nm, m
+
+
 # ----------------------------------------------------------------------------- matcher
 def descriptor_distance(a, b):
     a = _u8(a); b = _u8(b)

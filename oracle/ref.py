@@ -110,6 +110,15 @@ class Ref:
             uv[i] = (u.value, v.value)
         return uv, faces
 
+    def warp_extract_batch_out(self, fisheyes, m1, m2, mask, nfeatures, scaleFactor, nlevels, iniTh, minTh, nthreads, cap):
+        fisheyes = _u8(fisheyes); mask = _u8(mask); F = fisheyes.shape[0]
+        kps = np.zeros((F, cap), KP_DTYPE); desc = np.zeros((F, cap, 32), np.uint8); n = np.zeros(F, np.int32)
+        self.L.ref_set_camera(C.byref(self.cp)); self.L.ref_set_pins(0)
+        self.L.ref_warp_extract_batch_out.restype = C.c_long
+        self.L.ref_warp_extract_batch_out(_p(fisheyes), F, _p(m1), _p(m2), _p(mask), int(nfeatures), C.c_float(scaleFactor), int(nlevels), int(iniTh), int(minTh), int(nthreads), int(cap),
+                                          _p(kps), _p(desc), _p(n))
+        return kps, desc, n
+
     def descriptor_distance(self, a, b):
         a = _u8(a); b = _u8(b)
         return self.L.ref_descriptor_distance(_p(a), _p(b))

@@ -333,6 +333,37 @@ void ref_expr_neg_Rt_t(const float* R9, const float* t3, float* out3) {
     for (int i = 0; i < 3; i++) out3[i] = o.at<float>(i);
 }
 
+// same with per-frame outputs (kps / desc: nframes x cap) for the extract+match CPU baseline
+long ref_warp_extract_batch_out(const uint8_t* fisheyes, int nframes, const float* map1, const float* map2, const uint8_t* mask, int nfeatures, float scaleFactor, int nlevels,
+                                int iniTh, int minTh, int nthreads, int cap, cv::KeyPoint* kpsOut, uint8_t* descOut, int* nOut) {
+    CamModelGeneral* cam = CamModelGeneral::GetCamera();
+    const int W3 = cam->GetCubeFaceWidth() * 3, H3 = cam->GetCubeFaceHeight() * 3, Iw = cam->GetFisheyeWidth(), Ih = cam->GetFisheyeHeight();
+    std::vector<long> totals(nthreads, 0);
+    auto work = [&](int t) {
+        ORBextractor ex(nfeatures, scaleFactor, nlevels, iniTh, minTh);
+        cv::Mat canvas = cv::Mat::zeros(H3, W3, CV_8UC1), mk(H3, W3, CV_8UC1, (void*)mask), desc;
+        cv::Mat m1(H3, W3, CV_32F, (void*)map1), m2(H3, W3, CV_32F, (void*)map2);
+        std::vector<cv::KeyPoint> kps;
+        for (int f = t; f < nframes; f += nthreads) {
+            cv::Mat fe(Ih, Iw, CV_8UC1, (void*)(fisheyes + (size_t)f * Iw * Ih));
+            warp_into(canvas, fe, m1, m2);
+            ex(canvas, mk, kps, desc);
+            const int m = std::min((int)kps.size(), cap);
+            nOut[f] = m;
+            if (m) std::memcpy((void*)(kpsOut + (size_t)f * cap), kps.data(), (size_t)m * sizeof(cv::KeyPoint));
+            for (int i = 0; i < m; i++) std::memcpy(descOut + ((size_t)f * cap + i) * 32, desc.ptr<uchar>(i), 32);
+            totals[t] += m;
+        }
+    };
+    std::vector<std::thread> th;
+    for (int t = 1; t < nthreads; t++) th.emplace_back(work, t);
+    work(0);
+    for (auto& x : th) x.join();
+    long s = 0;
+    for (long v : totals) s += v;
+    return s;
+}
+
 // ORBMatcher::DescriptorDistance, src/ORBMatcher.cpp:951-967
 int ref_descriptor_distance(const uint8_t* a, const uint8_t* b) {
     cv::Mat ma(1, 32, CV_8UC1, (void*)a), mb(1, 32, CV_8UC1, (void*)b);
