@@ -18,7 +18,8 @@
 //   k_ba_backsub / k_ba_update / k_ba_scale / k_ba_restore   landmark back-substitution, oplus (with backup), gain-ratio scale
 // Multi-GPU: landmarks (with their edges) are sharded l % nranks; every rank forms its partial [S | g | bpr | chi2 | scale]
 // and the partials are summed either by one ncclAllReduce or by the one-shot NVLink kernel k_ba_xchg_reduce (peer pointers),
-// in fixed rank order so that every rank solves bit-identical systems.
+// in fixed rank order so that every rank solves bit-identical systems. Payloads are double-buffered by epoch parity: a rank may run one
+// exchange ahead of a peer that is still reading the previous one.
 // LM control flow (accept/reject, lambda schedule, ORB-SLAM2's stop rule, pbStopFlag) stays on the host like in the reference.
 #include <cooperative_groups.h>
 #include <dlfcn.h>
@@ -601,7 +602,7 @@ __global__ void __launch_bounds__(256) k_ba_xchg_reduce(XchgPeers P, unsigned ep
         volatile unsigned* mine = P.flags[P.rank];
         for (int r = 0; r < P.n; r++) {
             long long spins = 0;
-            while (mine[r] != epoch) { if (++spins > (1ll << 26)) { ok = 0; break; } __nanosleep(64); }
+            while ((int)(mine[r] - epoch) < 0) { if (++spins > (1ll << 26)) { ok = 0; break; } __nanosleep(64); }   // a fast peer may already be one epoch ahead
             if (!ok) break;
         }
         __threadfence_system();
@@ -697,7 +698,7 @@ static int setup_xchg(cslam_optimizer* o, size_t payloadBytes) {
     for (auto& p : o->peers) { if (p.base && !p.mine) cudaIpcCloseMemHandle(p.base); else if (p.base) cudaFree(p.base); }
     o->peers.assign(o->nranks, cslam_optimizer::Peer());
     void* mine = nullptr;
-    const size_t bytes = ((payloadBytes + 255) & ~(size_t)255) + XCHG_FLAG_BYTES;
+    const size_t bytes = 2 * ((payloadBytes + 255) & ~(size_t)255) + XCHG_FLAG_BYTES;   // two payload buffers (epoch parity) + the flag slots
     CSLAM_CUDA(cudaMalloc(&mine, bytes));
     CSLAM_CUDA(cudaMemset(mine, 0, bytes));
     cudaIpcMemHandle_t h;
@@ -753,7 +754,8 @@ struct BAHost {
     int* d_poseIdx = nullptr; uint8_t* d_ptAct = nullptr; uint8_t* d_flag = nullptr;
     double* Lt = nullptr; double* LDt = nullptr; int ldp = 0;
     double* red = nullptr;            // private reduce buffer [S | g | bpr | tail]
-    double* xmine = nullptr;          // this rank's exchange payload (one-shot path) - the Schur kernel writes there
+    double* HppFull = nullptr;        // multi-GPU: all-reduced copy of the pose blocks for computeLambdaInit
+    size_t xstride = 0;               // one-shot path: doubles between the two payload buffers of an exchange region
     int* d_xerr = nullptr;
     double lambda = -1, ni = 2; int nBad = 0; int iterations = 0, trials = 0;
     const volatile uint8_t* stop = nullptr;
@@ -774,8 +776,8 @@ struct BAHost {
         CSLAM_CUDA(cudaStreamSynchronize(o->stream));
         return 0;
     }
-    void bind() {   // partial system of this rank goes to `w` (exchange payload on the one-shot path), the reduced one lives in `red`
-        double* w = (o->nranks > 1 && useOneShot) ? xmine : red;
+    void bind(unsigned epoch = 0) {   // partial system of this rank goes to `w` (exchange payload of this epoch on the one-shot path), the reduced one lives in `red`
+        double* w = (o->nranks > 1 && useOneShot) ? (double*)o->peers[o->rank].base + (epoch & 1) * xstride : red;
         D.S = w; D.g = w + (size_t)D.n * D.n; D.bpr = D.g + D.n; D.tail = D.bpr + D.n;
     }
     BADev reducedView() const { BADev R = D; R.S = red; R.g = red + (size_t)D.n * D.n; R.bpr = R.g + D.n; R.tail = R.bpr + D.n; return R; }
@@ -813,10 +815,13 @@ struct BAHost {
     int lambda_init(double* lam) {
         int rc;
         CSLAM_CUDA(cudaMemsetAsync(D.scal + 2, 0, sizeof(double), o->stream));
-        if (o->nranks > 1 && D.nP > 0) {   // computeLambdaInit needs the full pose blocks: sum the partial diagonals once per optimize()
-            if ((rc = allreduce(D.Hpp, (size_t)D.nP * 36, NCCL_SUM))) return rc;
+        BADev M = D;
+        if (o->nranks > 1 && D.nP > 0) {   // computeLambdaInit needs the full pose blocks: sum a COPY of the partial blocks once per optimize()
+            CSLAM_CUDA(cudaMemcpyAsync(HppFull, D.Hpp, (size_t)D.nP * 36 * 8, cudaMemcpyDeviceToDevice, o->stream));
+            if ((rc = allreduce(HppFull, (size_t)D.nP * 36, NCCL_SUM))) return rc;
+            M.Hpp = HppFull;
         }
-        k_ba_maxdiag<<<grid(D.nP * 6 + D.nMP * 3), 256, 0, o->stream>>>(D); o->launches++;
+        k_ba_maxdiag<<<grid(D.nP * 6 + D.nMP * 3), 256, 0, o->stream>>>(M); o->launches++;
         if ((rc = allreduce(D.scal + 2, 1, NCCL_MAX))) return rc;
         if ((rc = fetch(D.scal, 4))) return rc;
         *lam = 1e-5 * o->h_scal[2];
@@ -828,15 +833,16 @@ struct BAHost {
         k_ba_dinv<<<grid(D.nMP), 256, 0, o->stream>>>(D, lambda); o->launches++;
         if (D.n > 0) {
             const bool multi = o->nranks > 1;
+            const unsigned ep = (multi && useOneShot) ? ++o->epoch : 0;
+            bind(ep);
             k_ba_schur<<<dim3(D.nQ, D.nQ), SCHUR_T, 0, o->stream>>>(D, multi ? 0.0 : lambda); o->launches++;
             BADev R = D;
             if (multi) {
                 R = reducedView();
                 if (useOneShot) {
                     XchgPeers P; P.n = o->nranks; P.rank = o->rank;
-                    const size_t off = (o->xchgBytes + 255) & ~(size_t)255;
-                    for (int r = 0; r < o->nranks; r++) { P.payload[r] = (const double*)o->peers[r].base; P.flags[r] = (volatile unsigned*)((char*)o->peers[r].base + off); }
-                    const unsigned ep = ++o->epoch;
+                    const size_t off = 2 * xstride * 8;
+                    for (int r = 0; r < o->nranks; r++) { P.payload[r] = (const double*)o->peers[r].base + (ep & 1) * xstride; P.flags[r] = (volatile unsigned*)((char*)o->peers[r].base + off); }
                     k_ba_xchg_signal<<<1, 32, 0, o->stream>>>(P, ep); o->launches++;
                     k_ba_xchg_reduce<<<std::min(148, grid((int)std::min<size_t>(payload(), 1u << 30))), 256, 0, o->stream>>>(P, ep, red, payload(), D.n, lambda, d_xerr); o->launches++;
                 } else {
@@ -1026,7 +1032,8 @@ extern "C" int cslam_local_ba(cslam_optimizer* o, cslam_ba_problem* p, const vol
             if (xr < 0) return xr;
         }
         H.useOneShot = o->oneShot && o->xchgBytes >= payloadMax * 8 && !getenv("CSLAM_BA_NCCL_ONLY");
-        if (H.useOneShot) H.xmine = (double*)o->peers[o->rank].base;
+        H.xstride = ((o->xchgBytes + 255) & ~(size_t)255) / 8;
+        if ((rc = dalloc(o, &H.HppFull, (size_t)std::max(nQ, 1) * 36))) return rc;
     }
     // ---- co-observation lists (once per call, all edges)
     if (nQ > 0) {
