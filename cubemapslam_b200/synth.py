@@ -228,3 +228,33 @@ def tracking_pair(seed=0, n=2000, faceW=650, motion=0.02, rot=0.01, mp_frac=0.8,
     mpObs = (rng.random(n) < 0.9).astype(np.int32)
     curTaken = (rng.random(len(kC)) < 0.03).astype(np.uint8)
     return dict(kLast=kL, dLast=dL, TcwLast=TcwL, hasMP=hasMP, Xw=Xw, mpObs=mpObs, kCur=kC, dCur=dC, TcwCur=TcwC, src=src, scale=scale, curTaken=curTaken, faceW=W)
+
+
+# ----------------------------------------------------------------------------- vocabulary tree (DBoW2 text format)
+def vocabulary(k=10, L=4, seed=0, stop_frac=0.01):
+    """A synthetic vocabulary tree in ORBvoc.txt's node order (breadth-first per parent, like DBoW2's saveToTextFile): arrays for nodes 1..n
+    (parent, is_leaf, 32-byte descriptor, weight). Children descriptors are the parent's with ~12 % of the bits flipped (a hierarchical
+    k-medians-like structure); leaf weights are idf-like positive numbers, `stop_frac` of the words have weight 0 (stopped words)."""
+    rng = np.random.default_rng(9000 + seed)
+    parent = []; leaf = []; desc = []; weight = []
+    frontier = [(0, rng.integers(0, 256, 32, dtype=np.uint8))]
+    for level in range(1, L + 1):
+        nxt = []
+        for pid, pd in frontier:
+            for _ in range(k):
+                d = pd ^ np.packbits(rng.random(256) < 0.12, bitorder="little")
+                parent.append(pid); leaf.append(1 if level == L else 0); desc.append(d)
+                weight.append(0.0 if (level == L and rng.random() < stop_frac) else (float(rng.uniform(0.5, 9.0)) if level == L else 0.0))
+                nxt.append((len(parent), d))
+        frontier = nxt
+    return dict(k=k, L=L, parent=np.array(parent, np.int32), is_leaf=np.array(leaf, np.uint8), desc=np.stack(desc), weight=np.array(weight, np.float64))
+
+
+def write_vocabulary_text(voc, path):
+    """ORBvoc.txt format (reference ThirdParty/DBoW2/DBoW2/TemplatedVocabulary.h:1337-1415): 'k L scoring weighting' then one line per node.
+    No trailing newline: the reference's `while(!f.eof())` loop would turn it into one more (garbage) child of the root."""
+    lines = ["%d %d 0 0" % (voc["k"], voc["L"])]
+    for i in range(len(voc["parent"])):
+        lines.append("%d %d %s %r" % (voc["parent"][i], voc["is_leaf"][i], " ".join(str(int(b)) for b in voc["desc"][i]), float(voc["weight"][i])))
+    with open(path, "w") as f:
+        f.write("\n".join(lines))

@@ -138,6 +138,23 @@ int cslam_search_by_bow_kf(cslam_matcher* m, const uint8_t* desc1, const float* 
                            const uint8_t* desc2, const float* ang2, const uint8_t* valid2, const int32_t* node2, int n2, int npairs,
                            float nnratio, int check_ori, int32_t* match12, int32_t* nmatches);
 
+/* ---------------------------------------------------------------------------------------------- vocabulary (DBoW2 transform)
+ * ORBVocabulary::transform(features, BowVector&, FeatureVector&, levelsup) as Frame::ComputeBoW / KeyFrame::ComputeBoW call it (src/Frame.cpp:719-726;
+ * ThirdParty/DBoW2/DBoW2/TemplatedVocabulary.h:1127-1262). The tree is given as flat arrays for nodes 1..n_nodes in ORBvoc.txt's line order (what
+ * TemplatedVocabulary::loadFromTextFile :1337-1415 reads): parent id, leaf flag, 32 descriptor bytes, weight; scoring L1_NORM, weighting TF_IDF.
+ * Outputs per frame (stride slots): node = FeatureVector node id of the feature at level L - levelsup (-1: stopped word) - exactly the per-feature node
+ * array cslam_search_by_bow takes -; bow_word / bow_val = the BowVector in map order (bow_count entries, L1-normalised doubles, bit-identical to DBoW2). */
+typedef struct cslam_vocabulary cslam_vocabulary;
+int cslam_vocabulary_create(cslam_vocabulary** out, int device, int k, int L, int n_nodes, const int32_t* parent, const uint8_t* is_leaf, const uint8_t* desc, const double* weight,
+                            int max_frames, int max_features);
+void cslam_vocabulary_destroy(cslam_vocabulary* v);
+void* cslam_vocabulary_stream(const cslam_vocabulary* v);
+int cslam_vocabulary_sync(cslam_vocabulary* v);
+int cslam_bow_transform(cslam_vocabulary* v, const uint8_t* desc, const int32_t* n, int stride, int nframes, int levelsup, int32_t* word /* may be NULL */, int32_t* node,
+                        int32_t* bow_word, double* bow_val, int32_t* bow_count);
+int cslam_bow_transform_dev(cslam_vocabulary* v, const uint8_t* desc, const int32_t* n, int stride, int nframes, int levelsup, int32_t* word, int32_t* leaf, int32_t* node,
+                            int32_t* bow_word, double* bow_val, int32_t* bow_count);
+
 /* ---------------------------------------------------------------------------------------------- tracker
  * The matcher on the steady-state frame path and the per-frame indexing it needs:
  *   Frame::ComputeKeyPointRays (src/Frame.cpp:746-760) + Frame::AssignFeaturesToGrid (:158-176)      -> cslam_frame_index

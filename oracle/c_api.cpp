@@ -5,6 +5,7 @@
 #include <thread>
 #include "ba.h"
 #include "cam_model.h"
+#include "bow.h"
 #include "cvprim.h"
 #include "frame_index.h"
 #include "orb_extractor.h"
@@ -204,6 +205,19 @@ int orc_area_rects(float x, float y, float r, int faceW, int faceH, int* rects) 
 }
 void orc_ray_to_cubemap(const float* xyz, int n, int faceW, int faceH, float* uv, int* faces) {
     for (int i = 0; i < n; i++) faces[i] = fi_ray_to_cubemap(xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2], faceW, faceH, uv[2 * i], uv[2 * i + 1]);
+}
+
+// ---- DBoW2 transform
+void* orc_voc_create(int k, int L, int n, const int* parent, const uint8_t* isLeaf, const uint8_t* desc, const double* weight) {
+    Vocabulary* v = new Vocabulary; v->build(k, L, n, parent, isLeaf, desc, weight); return v;
+}
+void orc_voc_destroy(void* v) { delete (Vocabulary*)v; }
+int orc_voc_transform(void* vv, const uint8_t* feats, int n, int levelsup, int* bowWord, double* bowVal, int* nodeOf, int* wordOf) {
+    std::vector<int> bw, no, wo; std::vector<double> bv;
+    ((Vocabulary*)vv)->transform(feats, n, levelsup, bw, bv, no, wo);
+    for (size_t i = 0; i < bw.size(); i++) { bowWord[i] = bw[i]; bowVal[i] = bv[i]; }
+    for (int i = 0; i < n; i++) { nodeOf[i] = no[i]; wordOf[i] = wo[i]; }
+    return (int)bw.size();
 }
 
 // ---- bundle adjustment

@@ -303,6 +303,28 @@ def ray_to_cubemap(xyz, faceW, faceH):
     return uv, faces
 
 
+# ----------------------------------------------------------------------------- DBoW2 transform
+class Vocabulary:
+    """Vocabulary tree from flat arrays (nodes 1..n in file order: parent, leaf flag, descriptor, weight); transform like DBoW2 (levelsup 4)."""
+
+    def __init__(self, k, L, parent, is_leaf, desc, weight):
+        parent = _i32(parent); is_leaf = _u8(is_leaf); desc = _u8(desc); weight = np.ascontiguousarray(weight, np.float64)
+        lib().orc_voc_create.restype = C.c_void_p
+        self._h = C.c_void_p(lib().orc_voc_create(int(k), int(L), len(parent), _p(parent), _p(is_leaf), _p(desc), _p(weight)))
+
+    def __del__(self):
+        try:
+            lib().orc_voc_destroy(self._h)
+        except Exception:
+            pass
+
+    def transform(self, feats, levelsup=4):
+        feats = _u8(feats); n = len(feats)
+        bw = np.zeros(max(n, 1), np.int32); bv = np.zeros(max(n, 1), np.float64); node = np.zeros(max(n, 1), np.int32); word = np.zeros(max(n, 1), np.int32)
+        m = lib().orc_voc_transform(self._h, _p(feats), n, int(levelsup), _p(bw), _p(bv), _p(node), _p(word))
+        return bw[:m].copy(), bv[:m].copy(), node[:n].copy(), word[:n].copy()
+
+
 # ----------------------------------------------------------------------------- bundle adjustment
 def local_ba(Tcw, kf_fixed, pts, eMP, eKF, kpxy, inv_sigma2, faceW, faceH, its1=5, its2=10, stop_flag=None):
     Tcw = _f32(Tcw).copy(); pts = _f32(pts).copy()

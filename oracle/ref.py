@@ -185,3 +185,29 @@ class RefFrame:
         buf = np.empty(8192, np.int32)
         n = self.ref.L.ref_frame_features_in_area(self._h, C.c_float(x), C.c_float(y), C.c_float(r), int(min_level), int(max_level), _p(buf), 8192)
         return buf[:n].copy()
+
+
+class RefVocabulary:
+    """The reference's ORBVocabulary (DBoW2 TemplatedVocabulary<FORB>) loaded from a text file in ORBvoc.txt's format."""
+
+    def __init__(self, path, variant="libref.so"):
+        self.L = lib(variant)
+        self.L.ref_voc_load.restype = C.c_void_p
+        self._h = C.c_void_p(self.L.ref_voc_load(str(path).encode()))
+        if not self._h:
+            raise RuntimeError("vocabulary load failed: " + str(path))
+
+    def __del__(self):
+        try:
+            self.L.ref_voc_destroy(self._h)
+        except Exception:
+            pass
+
+    def size(self):
+        return self.L.ref_voc_size(self._h)
+
+    def transform(self, feats, levelsup=4):
+        feats = _u8(feats); n = len(feats)
+        bw = np.zeros(max(n, 1), np.int32); bv = np.zeros(max(n, 1), np.float64); node = np.zeros(max(n, 1), np.int32)
+        m = self.L.ref_voc_transform(self._h, _p(feats), n, int(levelsup), _p(bw), _p(bv), _p(node))
+        return bw[:m].copy(), bv[:m].copy(), node[:n].copy()

@@ -364,6 +364,29 @@ long ref_warp_extract_batch_out(const uint8_t* fisheyes, int nframes, const floa
     return s;
 }
 
+// ---- DBoW2: ORBVocabulary (include/ORBVocabulary.h:35-36) loaded from a text file like System does (src/System.cpp:52-61), transform like Frame::ComputeBoW
+void* ref_voc_load(const char* path) {
+    ORBVocabulary* v = new ORBVocabulary();
+    if (!v->loadFromTextFile(path)) { delete v; return nullptr; }
+    return v;
+}
+void ref_voc_destroy(void* v) { delete (ORBVocabulary*)v; }
+int ref_voc_size(void* v) { return (int)((ORBVocabulary*)v)->size(); }
+// bowWord / bowVal: the BowVector in map order; nodeOf[i]: FeatureVector node of feature i (-1 if the feature is in no node list)
+int ref_voc_transform(void* vv, const uint8_t* feats, int n, int levelsup, int32_t* bowWord, double* bowVal, int32_t* nodeOf) {
+    ORBVocabulary* voc = (ORBVocabulary*)vv;
+    cv::Mat D(n, 32, CV_8UC1, (void*)feats);
+    std::vector<cv::Mat> vCurrentDesc = Converter::toDescriptorVector(D);   // src/Frame.cpp:723
+    DBoW2::BowVector bv; DBoW2::FeatureVector fv;
+    voc->transform(vCurrentDesc, bv, fv, levelsup);
+    int m = 0;
+    for (DBoW2::BowVector::const_iterator it = bv.begin(); it != bv.end(); ++it, ++m) { bowWord[m] = (int32_t)it->first; bowVal[m] = it->second; }
+    for (int i = 0; i < n; i++) nodeOf[i] = -1;
+    for (DBoW2::FeatureVector::const_iterator it = fv.begin(); it != fv.end(); ++it)
+        for (size_t k = 0; k < it->second.size(); k++) nodeOf[it->second[k]] = (int32_t)it->first;
+    return m;
+}
+
 // ORBMatcher::DescriptorDistance, src/ORBMatcher.cpp:951-967
 int ref_descriptor_distance(const uint8_t* a, const uint8_t* b) {
     cv::Mat ma(1, 32, CV_8UC1, (void*)a), mb(1, 32, CV_8UC1, (void*)b);
