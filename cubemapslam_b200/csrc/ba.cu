@@ -50,7 +50,7 @@ struct BADev {
     const int2* tuples;              // (a1, a2)
     double *Hpp, *bp, *Hll, *bl, *Hpl, *Dinv, *db, *xp, *xl;
     double *S, *g, *bpr, *tail;      // one contiguous exchange buffer: [S n*n | g n | bpr n | tail 4]; tail = chi2, scale, -, -
-    double* scal;                    // [0] chi2, [1] scale, [2] max diag (as bits), [3] solve flag
+    double* scal;                    // [0] chi2, [1] scale, [2] max diag (as bits), [3] solve flag, [4] lambda of the current trial
     double* part; unsigned* ticket;  // block partials + arrival counter of the deterministic grid reductions
     int robust; double delta, dsqr;
     int rank, nranks;                // landmark l is owned by rank l % nranks
@@ -208,7 +208,8 @@ __global__ void __launch_bounds__(256) k_ba_maxdiag(BADev D) {
 }
 
 // Dinv = (Hll + lambda I)^-1 (3x3 cofactors, like Eigen), db = Dinv * bl
-__global__ void __launch_bounds__(256) k_ba_dinv(BADev D, double lambda) {
+__global__ void __launch_bounds__(256) k_ba_dinv(BADev D) {
+    const double lambda = D.scal[4];
     const int l = blockIdx.x * blockDim.x + threadIdx.x;
     if (l >= D.nMP || !owned(D, l)) return;
     double* Dv = D.Dinv + 9 * (size_t)l;
@@ -315,7 +316,8 @@ __global__ void __launch_bounds__(128) k_ba_pairs_fill(BADev D, const long long*
 // Schur complement (block_solver.hpp:381-439), output-stationary: one CTA per pose pair accumulates its 6x6 block in registers over the
 // pair's co-observation list, then a fixed-shape reduction. The diagonal pair also forms g = bp - sum B (Dinv bl) and bpr = bp.
 static const int SCHUR_T = 128;
-__global__ void __launch_bounds__(SCHUR_T) k_ba_schur(BADev D, double lambdaDiag) {
+__global__ void __launch_bounds__(SCHUR_T) k_ba_schur(BADev D, int addLambda) {
+    const double lambdaDiag = addLambda ? D.scal[4] : 0.0;
     __shared__ double red[SCHUR_T / 32][44];
     const int q1 = blockIdx.y, q2 = blockIdx.x;
     if (q1 > q2) return;
@@ -396,8 +398,10 @@ __global__ void __launch_bounds__(SCHUR_T) k_ba_schur(BADev D, double lambdaDiag
 static const int LD_NB = 32;
 static const int SOLVE_T = 256;
 
-__global__ void __launch_bounds__(SOLVE_T) k_ba_solve(BADev D, double* __restrict__ Lt, double* __restrict__ LDt, int ldp) {
-    extern __shared__ double ysm[];                 // back substitution: y[n]
+// Panel staging: when both transposed panels (L and L*d, NB x rows each) fit in shared memory every CTA copies them there once per panel with
+// coalesced 16-byte L2 loads and the 4x2 register tiles of the trailing update read shared memory; otherwise the tiles stream from L2.
+__global__ void __launch_bounds__(SOLVE_T) k_ba_solve(BADev D, double* __restrict__ Lt, double* __restrict__ LDt, int ldp, int stage) {
+    extern __shared__ double dsm[];                 // [stage ? 2 * NB * ldp : 0] panels, then y[n] for the back substitution
     __shared__ double Pd[LD_NB][LD_NB + 1];         // diagonal block: L below the diagonal after (1)
     __shared__ double PDd[LD_NB][LD_NB + 1];        // L * d
     __shared__ double dvec[LD_NB];
@@ -406,6 +410,7 @@ __global__ void __launch_bounds__(SOLVE_T) k_ba_solve(BADev D, double* __restric
     const int C = cluster.num_blocks(), crank = cluster.block_rank();
     const int n = D.n, tid = threadIdx.x;
     double* A = D.S;
+    double* sL = dsm; double* sLD = dsm + (size_t)LD_NB * ldp;
     if (tid == 0) fail = 0;
     __syncthreads();
     for (int jb = 0; jb < n; jb += LD_NB) {
@@ -432,9 +437,10 @@ __global__ void __launch_bounds__(SOLVE_T) k_ba_solve(BADev D, double* __restric
             }
         }
         if (fail) break;   // block-uniform and identical in every CTA of the cluster (same data)
-        // (2) rows below the diagonal block (including the rhs row)
+        // (2) rows below the diagonal block (including the rhs row): a contiguous chunk of rows per CTA, one thread per row
         const int trR = rows - nb;
-        for (int rr = crank * SOLVE_T + tid; rr < trR; rr += C * SOLVE_T) {
+        const int chunk = (trR + C - 1) / C, r0c = crank * chunk, r1c = min(r0c + chunk, trR);
+        for (int rr = r0c + tid; rr < r1c; rr += SOLVE_T) {
             double* Arow = A + (size_t)(jb + nb + rr) * n + jb;
             double x[LD_NB];
 #pragma unroll
@@ -447,41 +453,63 @@ __global__ void __launch_bounds__(SOLVE_T) k_ba_solve(BADev D, double* __restric
                     for (int c2 = 0; c2 < c; c2++) v -= x[c2] * Pd[c][c2];
                     x[c] = v;
                     const double lv = v / dvec[c];
-                    Arow[c] = lv;
-                    Lt[(size_t)c * ldp + rr] = lv; LDt[(size_t)c * ldp + rr] = v;
+                    __stcg(Arow + c, lv);
+                    __stcg(Lt + (size_t)c * ldp + rr, lv); __stcg(LDt + (size_t)c * ldp + rr, v);
                 }
             }
         }
         // L of the diagonal block back into S (needed by the back substitution), by cluster rank 0
         if (crank == 0)
-            for (int i = tid; i < nb * nb; i += SOLVE_T) { const int r = i / nb, c = i - r * nb; if (r > c) A[(size_t)(jb + r) * n + jb + c] = Pd[r][c]; }
+            for (int i = tid; i < nb * nb; i += SOLVE_T) { const int r = i / nb, c = i - r * nb; if (r > c) __stcg(A + (size_t)(jb + r) * n + jb + c, Pd[r][c]); }
         cluster.sync();
         // (3) trailing update A[i][k] -= sum_c (L d)[i][c] L[k][c], rows i include the rhs row, columns k < trC, k <= i
         const int trC = n - jb - nb;
         if (trC > 0) {
+            const double* pL = Lt; const double* pLD = LDt;
+            if (stage) {
+                const int w2 = (trR + 1) >> 1;   // double2 words per panel row
+                for (int i = tid; i < LD_NB * w2; i += SOLVE_T) {
+                    const int c = i / w2, q = i - c * w2;
+                    if (c < nb) {
+                        reinterpret_cast<double2*>(sL + (size_t)c * ldp)[q] = __ldcg(reinterpret_cast<const double2*>(Lt + (size_t)c * ldp) + q);
+                        reinterpret_cast<double2*>(sLD + (size_t)c * ldp)[q] = __ldcg(reinterpret_cast<const double2*>(LDt + (size_t)c * ldp) + q);
+                    }
+                }
+                __syncthreads();
+                pL = sL; pLD = sLD;
+            }
             const int tR = (trR + 3) >> 2, tC = (trC + 1) >> 1;
             for (int i = crank * SOLVE_T + tid; i < tR * tC; i += C * SOLVE_T) {
                 const int br = i / tC, bc = i - br * tC;
                 const int r0 = 4 * br, k0 = 2 * bc;
                 if (k0 > r0 + 3) continue;   // tile entirely above the diagonal
                 double acc[4][2] = {{0, 0}, {0, 0}, {0, 0}, {0, 0}};
+                if (stage) {
 #pragma unroll 8
-                for (int c = 0; c < nb; c++) {
-                    const double2 bv = __ldcg(reinterpret_cast<const double2*>(Lt + (size_t)c * ldp + k0));
-                    const double2 a01 = __ldcg(reinterpret_cast<const double2*>(LDt + (size_t)c * ldp + r0));
-                    const double2 a23 = __ldcg(reinterpret_cast<const double2*>(LDt + (size_t)c * ldp + r0 + 2));
-                    acc[0][0] += a01.x * bv.x; acc[0][1] += a01.x * bv.y;
-                    acc[1][0] += a01.y * bv.x; acc[1][1] += a01.y * bv.y;
-                    acc[2][0] += a23.x * bv.x; acc[2][1] += a23.x * bv.y;
-                    acc[3][0] += a23.y * bv.x; acc[3][1] += a23.y * bv.y;
+                    for (int c = 0; c < nb; c++) {
+                        const double2 bv = *reinterpret_cast<const double2*>(pL + (size_t)c * ldp + k0);
+                        const double2 a01 = *reinterpret_cast<const double2*>(pLD + (size_t)c * ldp + r0);
+                        const double2 a23 = *reinterpret_cast<const double2*>(pLD + (size_t)c * ldp + r0 + 2);
+                        acc[0][0] += a01.x * bv.x; acc[0][1] += a01.x * bv.y; acc[1][0] += a01.y * bv.x; acc[1][1] += a01.y * bv.y;
+                        acc[2][0] += a23.x * bv.x; acc[2][1] += a23.x * bv.y; acc[3][0] += a23.y * bv.x; acc[3][1] += a23.y * bv.y;
+                    }
+                } else {
+#pragma unroll 8
+                    for (int c = 0; c < nb; c++) {
+                        const double2 bv = __ldcg(reinterpret_cast<const double2*>(pL + (size_t)c * ldp + k0));
+                        const double2 a01 = __ldcg(reinterpret_cast<const double2*>(pLD + (size_t)c * ldp + r0));
+                        const double2 a23 = __ldcg(reinterpret_cast<const double2*>(pLD + (size_t)c * ldp + r0 + 2));
+                        acc[0][0] += a01.x * bv.x; acc[0][1] += a01.x * bv.y; acc[1][0] += a01.y * bv.x; acc[1][1] += a01.y * bv.y;
+                        acc[2][0] += a23.x * bv.x; acc[2][1] += a23.x * bv.y; acc[3][0] += a23.y * bv.x; acc[3][1] += a23.y * bv.y;
+                    }
                 }
 #pragma unroll
                 for (int a = 0; a < 4; a++) {
                     const int r = r0 + a;
                     if (r >= trR) break;
                     double* dst = A + (size_t)(jb + nb + r) * n + jb + nb;
-                    if (k0 <= r && k0 < trC) dst[k0] -= acc[a][0];
-                    if (k0 + 1 <= r && k0 + 1 < trC) dst[k0 + 1] -= acc[a][1];
+                    if (k0 <= r && k0 < trC) __stcg(dst + k0, __ldcg(dst + k0) - acc[a][0]);
+                    if (k0 + 1 <= r && k0 + 1 < trC) __stcg(dst + k0 + 1, __ldcg(dst + k0 + 1) - acc[a][1]);
                 }
             }
         }
@@ -490,7 +518,7 @@ __global__ void __launch_bounds__(SOLVE_T) k_ba_solve(BADev D, double* __restric
     if (fail) { if (crank == 0 && tid == 0) D.scal[3] = 1.0; return; }
     if (crank != 0) return;
     // backward: L^T x = z, z = row n of L (= D^-1 L^-1 g); blocks of NB columns from the bottom
-    double* y = ysm;
+    double* y = dsm + (stage ? 2 * (size_t)LD_NB * ldp : 0);
     for (int i = tid; i < n; i += SOLVE_T) y[i] = __ldcg(A + (size_t)n * n + i);
     __syncthreads();
     for (int je = n; je > 0; je -= LD_NB) {
@@ -505,12 +533,15 @@ __global__ void __launch_bounds__(SOLVE_T) k_ba_solve(BADev D, double* __restric
             }
         }
         __syncthreads();
-        // rows above: y[i] -= sum_{j in block} L[j][i] x_j   (rows of L are contiguous: coalesced over i)
+        // rows above: y[i] -= sum_{j in block} L[j][i] x_j   (rows of L are contiguous: coalesced over i; all loads of a thread are independent)
         for (int i = tid; i < j0; i += SOLVE_T) {
-            double s = 0;
-#pragma unroll 8
-            for (int j = 0; j < nb; j++) s += __ldcg(A + (size_t)(j0 + j) * n + i) * y[j0 + j];
-            y[i] -= s;
+            double v[LD_NB];
+#pragma unroll
+            for (int j = 0; j < LD_NB; j++) v[j] = j < nb ? __ldcg(A + (size_t)(j0 + j) * n + i) : 0.0;
+            double sacc = 0;
+#pragma unroll
+            for (int j = 0; j < LD_NB; j++) if (j < nb) sacc += v[j] * y[j0 + j];
+            y[i] -= sacc;
         }
         __syncthreads();
     }
@@ -559,8 +590,9 @@ __global__ void __launch_bounds__(256) k_ba_restore(BADev D) {
 }
 
 // computeScale: sum_j x_j (lambda x_j + b_j); the pose part is added by rank 0 only (replicated), landmarks by their owner
-__global__ void __launch_bounds__(256) k_ba_scale(BADev D, double lambda, double* out) {
+__global__ void __launch_bounds__(256) k_ba_scale(BADev D, double* out) {
     __shared__ double sh[32];
+    const double lambda = D.scal[4];
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     double v = 0;
     if (i < D.n && D.rank == 0) v = D.xp[i] * (lambda * D.xp[i] + D.bpr[i]);
@@ -595,8 +627,9 @@ __global__ void k_ba_xchg_signal(XchgPeers P, unsigned epoch) {
         __threadfence_system();
     }
 }
-__global__ void __launch_bounds__(256) k_ba_xchg_reduce(XchgPeers P, unsigned epoch, double* dst, size_t count, int n, double lambda, int* err) {
+__global__ void __launch_bounds__(256) k_ba_xchg_reduce(XchgPeers P, unsigned epoch, double* dst, size_t count, int n, const double* lambdaPtr, int* err) {
     __shared__ int ok;
+    const double lambda = *lambdaPtr;
     if (threadIdx.x == 0) {
         ok = 1;
         volatile unsigned* mine = P.flags[P.rank];
@@ -650,6 +683,9 @@ static NcclApi* nccl_api() {
     return &api;
 }
 enum { NCCL_U8 = 1, NCCL_F64 = 8, NCCL_SUM = 0, NCCL_MAX = 2 };
+enum { BK_ERRORS = 0, BK_LIN_POINTS, BK_LIN_POSES, BK_DINV, BK_SCHUR, BK_XCHG, BK_SOLVE, BK_BACKSUB, BK_UPDATE, BK_SCALE, BK_END, BK_COUNT };
+static const char* kBaKindNames[BK_COUNT] = {"k_ba_errors", "k_ba_lin_points", "k_ba_lin_poses", "k_ba_dinv", "k_ba_schur", "exchange", "k_ba_solve", "k_ba_backsub", "k_ba_update", "k_ba_scale", "end"};
+
 
 extern "C" int cslam_optimizer_create(cslam_optimizer** out, int device) {
     if (!out) return CSLAM_E_BADARG;
@@ -663,7 +699,8 @@ extern "C" int cslam_optimizer_create(cslam_optimizer** out, int device) {
     }
     if (const char* e = getenv("CSLAM_SOLVE_CLUSTER")) o->clusterSize = std::max(1, std::min(atoi(e), 16));
     if (o->clusterSize > 8) cudaFuncSetAttribute(k_ba_solve, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
-    cudaFuncSetAttribute(k_ba_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024);
+    cudaFuncSetAttribute(k_ba_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, 204 * 1024);
+    if (const char* e = getenv("CSLAM_BA_GRAPH")) o->useGraphs = atoi(e) != 0;
     *out = o;
     return CSLAM_OK;
 }
@@ -680,6 +717,19 @@ extern "C" void cslam_optimizer_destroy(cslam_optimizer* o) {
     delete o;
 }
 extern "C" int64_t cslam_optimizer_launches(const cslam_optimizer* o) { return o ? o->launches : 0; }
+extern "C" int cslam_optimizer_set_timing(cslam_optimizer* o, int enable) {
+    if (!o) return CSLAM_E_BADARG;
+    CSLAM_CUDA(cudaSetDevice(o->device));
+    if (enable && o->ev.empty()) { o->ev.resize(64); o->evKind.resize(64); for (auto& e : o->ev) CSLAM_CUDA(cudaEventCreate(&e)); }
+    o->timing = enable != 0; o->evUsed = 0;
+    for (int i = 0; i < 16; i++) { o->kindMs[i] = 0; o->kindCount[i] = 0; }
+    return CSLAM_OK;
+}
+extern "C" int cslam_optimizer_get_timing(const cslam_optimizer* o, int kind, const char** name, double* ms, int64_t* count) {
+    if (!o || kind < 0 || kind >= BK_END) return CSLAM_E_BADARG;
+    *name = kBaKindNames[kind]; *ms = o->kindMs[kind]; *count = o->kindCount[kind];
+    return CSLAM_OK;
+}
 
 extern "C" int cslam_nccl_unique_id(uint8_t id128[128]) {
     NcclApi* a = nccl_api();
@@ -796,6 +846,7 @@ struct BAHost {
         CSLAM_CUDA(cudaMemcpyAsync(D.level, level.data(), D.nE, cudaMemcpyHostToDevice, o->stream));
         nActive = 0; for (int e = 0; e < D.nE; e++) nActive += level[e] == 0;
         bind();
+        drop_graph();   // the captured trial bakes in nP / n / the level array's meaning
         return 0;
     }
     int errors_chi2(double* chi) {   // computeActiveErrors + activeRobustChi2
@@ -808,6 +859,7 @@ struct BAHost {
     }
     int build_system() {
         k_ba_lin_points<<<grid(D.nMP, 128), 128, 0, o->stream>>>(D); o->launches++;
+        tick(BK_LIN_POSES);
         if (D.nQ > 0) { k_ba_lin_poses<<<D.nQ, 256, 0, o->stream>>>(D); o->launches++; }
         CSLAM_CUDA(cudaGetLastError());
         return 0;
@@ -827,61 +879,115 @@ struct BAHost {
         *lam = 1e-5 * o->h_scal[2];
         return 0;
     }
-    // one LM trial's linear solve (BlockSolver::solve)
-    int solve() {
+    // ---- optional per-kernel timing (cslam_optimizer_set_timing): CUDA events between launches, accumulated per kernel kind
+    void tick(int kind) {
+        if (!o->timing || o->evUsed >= (int)o->ev.size()) return;
+        cudaEventRecord(o->ev[o->evUsed], o->stream); o->evKind[o->evUsed++] = kind;
+    }
+    void collect() {
+        for (int i = 0; i + 1 < o->evUsed; i++) {
+            float ms = 0;
+            if (o->evKind[i] != BK_END && cudaEventElapsedTime(&ms, o->ev[i], o->ev[i + 1]) == cudaSuccess) { o->kindMs[o->evKind[i]] += ms; o->kindCount[o->evKind[i]]++; }
+        }
+        o->evUsed = 0;
+    }
+    // One LM trial on the stream: lambda -> device, BlockSolver::solve (Dinv, Schur, [exchange], reduced solve, back substitution), push + oplus,
+    // computeActiveErrors + activeRobustChi2, computeScale, the four scalars -> pinned host memory. Single-GPU trials are replayed as ONE CUDA graph.
+    int enqueue_trial() {
         int rc;
-        k_ba_dinv<<<grid(D.nMP), 256, 0, o->stream>>>(D, lambda); o->launches++;
+        CSLAM_CUDA(cudaMemcpyAsync(D.scal + 4, o->h_scal + 8, sizeof(double), cudaMemcpyHostToDevice, o->stream));   // h_scal[8] = lambda
+        tick(BK_DINV);
+        k_ba_dinv<<<grid(D.nMP), 256, 0, o->stream>>>(D); o->launches++;
+        BADev SV = D;
         if (D.n > 0) {
             const bool multi = o->nranks > 1;
             const unsigned ep = (multi && useOneShot) ? ++o->epoch : 0;
             bind(ep);
-            k_ba_schur<<<dim3(D.nQ, D.nQ), SCHUR_T, 0, o->stream>>>(D, multi ? 0.0 : lambda); o->launches++;
+            tick(BK_SCHUR);
+            k_ba_schur<<<dim3(D.nQ, D.nQ), SCHUR_T, 0, o->stream>>>(D, multi ? 0 : 1); o->launches++;
             BADev R = D;
             if (multi) {
                 R = reducedView();
+                tick(BK_XCHG);
                 if (useOneShot) {
                     XchgPeers P; P.n = o->nranks; P.rank = o->rank;
                     const size_t off = 2 * xstride * 8;
                     for (int r = 0; r < o->nranks; r++) { P.payload[r] = (const double*)o->peers[r].base + (ep & 1) * xstride; P.flags[r] = (volatile unsigned*)((char*)o->peers[r].base + off); }
                     k_ba_xchg_signal<<<1, 32, 0, o->stream>>>(P, ep); o->launches++;
-                    k_ba_xchg_reduce<<<std::min(148, grid((int)std::min<size_t>(payload(), 1u << 30))), 256, 0, o->stream>>>(P, ep, red, payload(), D.n, lambda, d_xerr); o->launches++;
+                    k_ba_xchg_reduce<<<std::min(148, grid((int)std::min<size_t>(payload(), 1u << 30))), 256, 0, o->stream>>>(P, ep, red, payload(), D.n, D.scal + 4, d_xerr); o->launches++;
                 } else {
                     CSLAM_CUDA(cudaMemcpyAsync(red, D.S, payload() * 8, cudaMemcpyDeviceToDevice, o->stream));
                     if ((rc = allreduce(red, payload(), NCCL_SUM))) return rc;
                     k_ba_add_lambda_launch(R);
                 }
+                SV.bpr = R.bpr;
             }
             CSLAM_CUDA(cudaMemsetAsync(D.scal + 3, 0, sizeof(double), o->stream));
+            tick(BK_SOLVE);
+            const size_t panel = 2 * (size_t)LD_NB * ldp * 8, ybytes = (size_t)D.n * 8;
+            const int stage = panel + ybytes <= 200 * 1024 ? 1 : 0;
             cudaLaunchConfig_t cfg = {};
-            cfg.gridDim = dim3(o->clusterSize); cfg.blockDim = dim3(SOLVE_T); cfg.dynamicSmemBytes = (size_t)D.n * 8; cfg.stream = o->stream;
+            cfg.gridDim = dim3(o->clusterSize); cfg.blockDim = dim3(SOLVE_T); cfg.dynamicSmemBytes = (stage ? panel : 0) + ybytes; cfg.stream = o->stream;
             cudaLaunchAttribute at[1];
             at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = o->clusterSize; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
             cfg.attrs = at; cfg.numAttrs = 1;
-            CSLAM_CUDA(cudaLaunchKernelEx(&cfg, k_ba_solve, R, Lt, LDt, ldp)); o->launches++;
-            solvedView = R;
+            CSLAM_CUDA(cudaLaunchKernelEx(&cfg, k_ba_solve, R, Lt, LDt, ldp, stage)); o->launches++;
         }
+        tick(BK_BACKSUB);
         k_ba_backsub<<<grid(D.nMP, 128), 128, 0, o->stream>>>(D); o->launches++;
+        tick(BK_UPDATE);
+        k_ba_update<<<grid(std::max(D.nKF, D.nMP)), 256, 0, o->stream>>>(D); o->launches++;
+        tick(BK_ERRORS);
+        k_ba_errors<<<grid(D.nE), 256, 0, o->stream>>>(D, D.scal); o->launches++;
+        tick(BK_SCALE);
+        k_ba_scale<<<grid(D.n + 3 * D.nMP), 256, 0, o->stream>>>(SV, D.scal + 1); o->launches++;
+        tick(BK_END);
+        if ((rc = allreduce(D.scal, 2, NCCL_SUM))) return rc;
+        CSLAM_CUDA(cudaMemcpyAsync(o->h_scal, D.scal, 4 * sizeof(double), cudaMemcpyDeviceToHost, o->stream));
         CSLAM_CUDA(cudaGetLastError());
         return 0;
     }
-    BADev solvedView;
+    cudaGraphExec_t trialGraph = nullptr;
+    void drop_graph() { if (trialGraph) { cudaGraphExecDestroy(trialGraph); trialGraph = nullptr; } }
+    int run_trial() {
+        int rc;
+        o->h_scal[8] = lambda;
+        const bool useGraph = o->nranks == 1 && !o->timing && o->useGraphs;
+        if (useGraph) {
+            if (!trialGraph) {
+                cudaGraph_t g = nullptr;
+                const int64_t l0 = o->launches;
+                CSLAM_CUDA(cudaStreamBeginCapture(o->stream, cudaStreamCaptureModeThreadLocal));
+                rc = enqueue_trial();
+                cudaError_t ce = cudaStreamEndCapture(o->stream, &g);
+                if (rc) { if (g) cudaGraphDestroy(g); return rc; }
+                CSLAM_CUDA(ce);
+                CSLAM_CUDA(cudaGraphInstantiate(&trialGraph, g, 0));
+                cudaGraphDestroy(g);
+                launchesPerTrial = o->launches - l0; o->launches = l0;
+            }
+            CSLAM_CUDA(cudaGraphLaunch(trialGraph, o->stream));
+            o->launches += launchesPerTrial;
+        } else if ((rc = enqueue_trial())) return rc;
+        CSLAM_CUDA(cudaStreamSynchronize(o->stream));
+        if (o->timing) collect();
+        return 0;
+    }
+    int64_t launchesPerTrial = 0;
     void k_ba_add_lambda_launch(const BADev& R);
     // OptimizationAlgorithmLevenberg::solve ; result 0 OK, 1 Terminate
     int lm_iteration(int iteration, int* result) {
         int rc; double currentChi = 0;
+        tick(BK_ERRORS);
         if ((rc = errors_chi2(&currentChi))) return rc;
         const double iniChi = currentChi; double tempChi = currentChi;
+        tick(BK_LIN_POINTS);
         if ((rc = build_system())) return rc;
+        tick(BK_END);
         if (iteration == 0) { if ((rc = lambda_init(&lambda))) return rc; ni = 2; nBad = 0; }
         double rho = 0; int qmax = 0; int accepted = 0;
         do {
-            if ((rc = solve())) return rc;
-            k_ba_update<<<grid(std::max(D.nKF, D.nMP)), 256, 0, o->stream>>>(D); o->launches++;
-            k_ba_errors<<<grid(D.nE), 256, 0, o->stream>>>(D, D.scal); o->launches++;
-            BADev SV = D; if (D.n > 0 && o->nranks > 1) { SV.bpr = solvedView.bpr; }
-            k_ba_scale<<<grid(D.n + 3 * D.nMP), 256, 0, o->stream>>>(SV, lambda, D.scal + 1); o->launches++;
-            if ((rc = allreduce(D.scal, 2, NCCL_SUM))) return rc;
-            if ((rc = fetch(D.scal, 4))) return rc;
+            if ((rc = run_trial())) return rc;
             tempChi = o->h_scal[0];
             bool ok2 = o->h_scal[3] == 0.0;
             trials++;
@@ -1060,6 +1166,7 @@ extern "C" int cslam_local_ba(cslam_optimizer* o, cslam_ba_problem* p, const vol
         if ((rc = H.optimize(its2))) return rc;
     }
     if ((rc = H.classify(flags))) return rc;
+    H.drop_graph();
     // ---- write back (src/Optimizer.cpp:432-450): float32 poses / points; with landmark sharding every rank holds its own points
     if (o->nranks > 1) {
         k_ba_mask_points<<<H.grid(nMP), 256, 0, o->stream>>>(D); o->launches++;

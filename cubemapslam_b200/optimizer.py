@@ -30,6 +30,18 @@ class Optimizer:
     def launches(self):
         return lib().cslam_optimizer_launches(self._h)
 
+    def set_timing(self, on):
+        check(lib().cslam_optimizer_set_timing(self._h, int(bool(on))))
+
+    def timing(self):
+        out = {}
+        for k in range(10):
+            name = C.c_char_p(); ms = C.c_double(); cnt = C.c_int64()
+            check(lib().cslam_optimizer_get_timing(self._h, k, C.byref(name), C.byref(ms), C.byref(cnt)))
+            if cnt.value:
+                out[name.value.decode()] = (ms.value, cnt.value)
+        return out
+
     @staticmethod
     def nccl_unique_id():
         buf = np.zeros(128, np.uint8)

@@ -238,6 +238,10 @@ typedef struct cslam_optimizer cslam_optimizer;
 int cslam_optimizer_create(cslam_optimizer** out, int device);
 void cslam_optimizer_destroy(cslam_optimizer* o);
 int64_t cslam_optimizer_launches(const cslam_optimizer* o);
+/* Per-kernel device timing of cslam_local_ba for bench.py's roofline block (CUDA events between launches; disables the CUDA-graph replay while on).
+ * kind 0..9 = k_ba_errors, k_ba_lin_points, k_ba_lin_poses, k_ba_dinv, k_ba_schur, exchange, k_ba_solve, k_ba_backsub, k_ba_update, k_ba_scale. */
+int cslam_optimizer_set_timing(cslam_optimizer* o, int enable);
+int cslam_optimizer_get_timing(const cslam_optimizer* o, int kind, const char** name, double* ms, int64_t* count);
 /* Landmark-sharded multi-GPU BA: every rank calls with the SAME problem; rank r owns landmarks l % nranks == r and
  * all-reduces the reduced camera system over NCCL. id128: ncclUniqueId bytes from cslam_nccl_unique_id on rank 0. */
 int cslam_nccl_unique_id(uint8_t id128[128]);

@@ -71,6 +71,13 @@ def test_pose_optimization_on_reference_frame(oracle, dropin):
     L, cfg, cp = dropin
     for seed in (5, 6):
         q = synth.pose_problem(n=300, faceW=450, seed=seed, outlier_frac=0.15)
+        # Optimizer::PoseOptimization skips correspondences whose key-point ray lies outside the field of view (src/Optimizer.cpp:84-86): feed both
+        # sides only correspondences that pass it, so that the oracle (which takes its edges as given) sees the same edge set
+        kp0 = np.zeros(len(q["Xw"]), KP); kp0["x"] = q["kpxy"][:, 0]; kp0["y"] = q["kpxy"][:, 1]
+        rays, _ = oracle.key_point_rays(kp0, 450, 450)
+        a = np.float32(cfg["Camera.fov"]) / np.float32(2) * (np.float32(3.1415926535897932384626) / np.float32(180))
+        keep = rays[:, 2] >= np.float32(np.cos(np.float64(a)))
+        q = dict(q, Xw=q["Xw"][keep], kpxy=q["kpxy"][keep], inv_sigma2=q["inv_sigma2"][keep])
         n = len(q["Xw"])
         octave = np.zeros(n, np.int32)
         T = np.ascontiguousarray(q["Tcw"], np.float32).copy(); out = np.zeros(n, np.uint8)
@@ -86,6 +93,13 @@ def test_local_bundle_adjustment_on_reference_map(oracle, dropin):
     covisible with the current one (every point is seen by all 6), so the local window is the whole problem and equals the oracle's input."""
     L, cfg, cp = dropin
     p = synth.ba_problem(nKF=6, nMP=400, kmin=6, kmax=6, faceW=450, seed=21, radius=1.5)
+    # the reference skips observations whose key-point ray is outside the field of view (src/Optimizer.cpp:323-325): drop them up front on both sides
+    kp0 = np.zeros(len(p["eMP"]), KP); kp0["x"] = p["kpxy"][:, 0]; kp0["y"] = p["kpxy"][:, 1]
+    rays, _ = oracle.key_point_rays(kp0, 450, 450)
+    a = np.float32(cfg["Camera.fov"]) / np.float32(2) * (np.float32(3.1415926535897932384626) / np.float32(180))
+    keep = rays[:, 2] >= np.float32(np.cos(np.float64(a)))
+    for key in ("eMP", "eKF", "kpxy", "inv_sigma2"):
+        p[key] = np.ascontiguousarray(p[key][keep])
     nKF, nMP, nE = 6, 400, len(p["eMP"])
     rng = np.random.default_rng(2)
     octave = rng.integers(0, 8, nE).astype(np.int32)
