@@ -52,6 +52,7 @@ struct BADev {
     double *S, *g, *bpr, *tail;      // one contiguous exchange buffer: [S n*n | g n | bpr n | tail 4]; tail = chi2, scale, -, -
     double* scal;                    // [0] chi2, [1] scale, [2] max diag (as bits), [3] solve flag, [4] lambda of the current trial
     double* part; unsigned* ticket;  // block partials + arrival counter of the deterministic grid reductions
+    double* posePart; unsigned* poseTicket;   // k_ba_lin_poses: slice sums [nQ][POSE_SPLIT][27] + arrival counter per pose
     int robust; double delta, dsqr;
     int rank, nranks;                // landmark l is owned by rank l % nranks
 };
@@ -116,11 +117,13 @@ __device__ __forceinline__ void linearize_edge(const BADev& D, int e, bool needP
 }
 
 // buildSystem, landmark side (base_binary_edge.hpp:55-120): Hll, bl of one landmark accumulated in registers in edge order, Hpl per edge
+static const int LM_LANES = 4;   // lanes that share one landmark in k_ba_lin_points / k_ba_backsub (edge a of the landmark goes to lane a % 4)
 __global__ void __launch_bounds__(128) k_ba_lin_points(BADev D) {
-    const int l = blockIdx.x * blockDim.x + threadIdx.x;
-    if (l >= D.nMP || !owned(D, l)) return;
+    const int l = (blockIdx.x * blockDim.x + threadIdx.x) / LM_LANES, sub = threadIdx.x % LM_LANES;
+    const bool mine = l < D.nMP && owned(D, l);
     double H[6] = {0, 0, 0, 0, 0, 0}, b[3] = {0, 0, 0};
-    for (int e = D.lmStart[l]; e < D.lmStart[l + 1]; e++) {
+    const int eBeg = mine ? D.lmStart[l] : 0, eEnd = mine ? D.lmStart[l + 1] : 0;
+    for (int e = eBeg + sub; e < eEnd; e += LM_LANES) {
         double* B = D.Hpl + 18 * (size_t)e;
         const int pi = D.poseIdx[D.eKF[e]];
         if (D.level[e] != 0) {   // inactive edges contribute zero blocks (the co-observation lists are built once per call)
@@ -147,20 +150,30 @@ __global__ void __launch_bounds__(128) k_ba_lin_points(BADev D) {
             for (int i = 0; i < 18; i++) B[i] = 0.0;
         }
     }
+    // fixed-shape sum over the 4 lanes of the landmark (all 32 lanes of the warp take part)
+#pragma unroll
+    for (int i = 0; i < 6; i++) { H[i] += __shfl_xor_sync(0xffffffffu, H[i], 1); H[i] += __shfl_xor_sync(0xffffffffu, H[i], 2); }
+#pragma unroll
+    for (int i = 0; i < 3; i++) { b[i] += __shfl_xor_sync(0xffffffffu, b[i], 1); b[i] += __shfl_xor_sync(0xffffffffu, b[i], 2); }
+    if (!mine || sub) return;
     double* Hl = D.Hll + 9 * (size_t)l;
     Hl[0] = H[0]; Hl[1] = H[1]; Hl[2] = H[2]; Hl[3] = H[1]; Hl[4] = H[3]; Hl[5] = H[4]; Hl[6] = H[2]; Hl[7] = H[4]; Hl[8] = H[5];
     D.bl[3 * l] = b[0]; D.bl[3 * l + 1] = b[1]; D.bl[3 * l + 2] = b[2];
 }
 
-// buildSystem, pose side: CTA per candidate pose over its edge list; 21 unique entries of Hpp + 6 of bp
+// buildSystem, pose side: POSE_SPLIT CTAs per candidate pose, each over a slice of the pose's edge list; 21 unique entries of Hpp + 6 of bp.
+// Slice sums go to posePart[q][slice][27]; the last CTA of the pose to arrive adds the slices in slice order (fixed shape -> reproducible).
+static const int POSE_SPLIT = 8;
 __global__ void __launch_bounds__(256) k_ba_lin_poses(BADev D) {
     __shared__ double red[8][28];
-    const int k = D.kfOfQ[blockIdx.x], p = D.poseIdx[k];
+    __shared__ bool last;
+    const int qi = blockIdx.x, sl = blockIdx.y;
+    const int k = D.kfOfQ[qi], p = D.poseIdx[k];
     if (p < 0) return;
     double acc[27];
 #pragma unroll
     for (int i = 0; i < 27; i++) acc[i] = 0.0;
-    for (int q = D.peStart[k] + threadIdx.x; q < D.peStart[k + 1]; q += blockDim.x) {
+    for (int q = D.peStart[k] + sl * 256 + threadIdx.x; q < D.peStart[k + 1]; q += POSE_SPLIT * 256) {
         const int e = D.peList[q];
         if (D.level[e] != 0 || !owned(D, D.eMP[e])) continue;
         EdgeLin L;
@@ -182,11 +195,24 @@ __global__ void __launch_bounds__(256) k_ba_lin_poses(BADev D) {
         if (lane == 0) red[w][i] = v;
     }
     __syncthreads();
+    double* mine = D.posePart + ((size_t)qi * POSE_SPLIT + sl) * 27;
     if (threadIdx.x < 27) {
         double s = 0;
         for (int ww = 0; ww < 8; ww++) s += red[ww][threadIdx.x];
+        __stcg(mine + threadIdx.x, s);
+    }
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) last = atomicAdd(D.poseTicket + qi, 1u) == POSE_SPLIT - 1;
+    __syncthreads();
+    if (!last) return;
+    __threadfence();
+    if (threadIdx.x < 27) {
+        double s = 0;
+        for (int j = 0; j < POSE_SPLIT; j++) s += __ldcg(D.posePart + ((size_t)qi * POSE_SPLIT + j) * 27 + threadIdx.x);
         red[0][threadIdx.x] = s;
     }
+    if (threadIdx.x == 0) D.poseTicket[qi] = 0;
     __syncthreads();
     if (threadIdx.x < 36) {
         const int a = threadIdx.x / 6, b = threadIdx.x % 6, lo = min(a, b), hi = max(a, b);
@@ -315,7 +341,9 @@ __global__ void __launch_bounds__(128) k_ba_pairs_fill(BADev D, const long long*
 
 // Schur complement (block_solver.hpp:381-439), output-stationary: one CTA per pose pair accumulates its 6x6 block in registers over the
 // pair's co-observation list, then a fixed-shape reduction. The diagonal pair also forms g = bp - sum B (Dinv bl) and bpr = bp.
-static const int SCHUR_T = 128;
+// Two threads share a tuple (rows 0-2 / rows 3-5 of the 6x6 block): 18 + 3 accumulators per thread keep the kernel at a register count
+// that lets the list loads of many tuples be in flight per SM (the kernel is L2-latency bound, the Hpl / Dinv blocks are L2 resident).
+static const int SCHUR_T = 256;
 __global__ void __launch_bounds__(SCHUR_T) k_ba_schur(BADev D, int addLambda) {
     const double lambdaDiag = addLambda ? D.scal[4] : 0.0;
     __shared__ double red[SCHUR_T / 32][44];
@@ -324,24 +352,25 @@ __global__ void __launch_bounds__(SCHUR_T) k_ba_schur(BADev D, int addLambda) {
     const int p1 = D.poseIdx[D.kfOfQ[q1]], p2 = D.poseIdx[D.kfOfQ[q2]];
     if (p1 < 0 || p2 < 0) return;
     const bool diag = q1 == q2;
-    double acc[42];
+    const int h = threadIdx.x & 1;
+    double acc[21];
 #pragma unroll
-    for (int i = 0; i < 42; i++) acc[i] = 0.0;
+    for (int i = 0; i < 21; i++) acc[i] = 0.0;
     const long long beg = D.pairStart[(size_t)q1 * D.nQ + q2], end = D.pairStart[(size_t)q1 * D.nQ + q2 + 1];
-    for (long long t = beg + threadIdx.x; t < end; t += SCHUR_T) {
+    for (long long t = beg + (threadIdx.x >> 1); t < end; t += SCHUR_T / 2) {
         const int2 tp = D.tuples[t];
         const int l = D.eMP[tp.x];
         if (!owned(D, l)) continue;
-        const double* B1 = D.Hpl + 18 * (size_t)tp.x;
+        const double* B1 = D.Hpl + 18 * (size_t)tp.x + 9 * h;
         const double* B2 = D.Hpl + 18 * (size_t)tp.y;
         const double* Di = D.Dinv + 9 * (size_t)l;
-        double b1[18], di[9], b2[18];
+        double b1[9], di[9], b2[18];
 #pragma unroll
-        for (int i = 0; i < 18; i++) { b1[i] = B1[i]; b2[i] = B2[i]; }
+        for (int i = 0; i < 9; i++) { b1[i] = B1[i]; di[i] = Di[i]; }
 #pragma unroll
-        for (int i = 0; i < 9; i++) di[i] = Di[i];
+        for (int i = 0; i < 18; i++) b2[i] = B2[i];
 #pragma unroll
-        for (int i = 0; i < 6; i++) {
+        for (int i = 0; i < 3; i++) {
             const double t0 = b1[3 * i] * di[0] + b1[3 * i + 1] * di[3] + b1[3 * i + 2] * di[6];
             const double t1 = b1[3 * i] * di[1] + b1[3 * i + 1] * di[4] + b1[3 * i + 2] * di[7];
             const double t2 = b1[3 * i] * di[2] + b1[3 * i + 1] * di[5] + b1[3 * i + 2] * di[8];
@@ -351,17 +380,18 @@ __global__ void __launch_bounds__(SCHUR_T) k_ba_schur(BADev D, int addLambda) {
         if (diag) {
             const double d0 = D.db[3 * l], d1 = D.db[3 * l + 1], d2 = D.db[3 * l + 2];
 #pragma unroll
-            for (int i = 0; i < 6; i++) acc[36 + i] += b1[3 * i] * d0 + b1[3 * i + 1] * d1 + b1[3 * i + 2] * d2;
+            for (int i = 0; i < 3; i++) acc[18 + i] += b1[3 * i] * d0 + b1[3 * i + 1] * d1 + b1[3 * i + 2] * d2;
         }
     }
+    // lanes of equal parity hold the same rows: xor offsets 16 .. 2 leave the row sums in lanes 0 (rows 0-2) and 1 (rows 3-5)
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
 #pragma unroll
-    for (int i = 0; i < 42; i++) {
-        if (i >= 36 && !diag) break;
+    for (int i = 0; i < 21; i++) {
+        if (i >= 18 && !diag) break;
         double v = acc[i];
 #pragma unroll
-        for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-        if (lane == 0) red[w][i] = v;
+        for (int o = 16; o > 1; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if (lane < 2) red[w][i < 18 ? 18 * lane + i : 36 + 3 * lane + (i - 18)] = v;
     }
     __syncthreads();
     const int n = D.n;
@@ -400,10 +430,11 @@ static const int SOLVE_T = 256;
 
 // Panel staging: when both transposed panels (L and L*d, NB x rows each) fit in shared memory every CTA copies them there once per panel with
 // coalesced 16-byte L2 loads and the 4x2 register tiles of the trailing update read shared memory; otherwise the tiles stream from L2.
-__global__ void __launch_bounds__(SOLVE_T) k_ba_solve(BADev D, double* __restrict__ Lt, double* __restrict__ LDt, int ldp, int stage) {
+__global__ void __launch_bounds__(SOLVE_T) k_ba_solve(BADev D, double* __restrict__ Lt, double* __restrict__ LDt, int ldp, int stage, long long* prof) {
     extern __shared__ double dsm[];                 // [stage ? 2 * NB * ldp : 0] panels, then y[n] for the back substitution
     __shared__ double Pd[LD_NB][LD_NB + 1];         // diagonal block: L below the diagonal after (1)
     __shared__ double PDd[LD_NB][LD_NB + 1];        // L * d
+    __shared__ double Ld[LD_NB][LD_NB + 1];         // L of the diagonal block while Pd still holds the working columns
     __shared__ double dvec[LD_NB];
     __shared__ int fail;
     cg::cluster_group cluster = cg::this_cluster();
@@ -413,6 +444,10 @@ __global__ void __launch_bounds__(SOLVE_T) k_ba_solve(BADev D, double* __restric
     double* sL = dsm; double* sLD = dsm + (size_t)LD_NB * ldp;
     if (tid == 0) fail = 0;
     __syncthreads();
+    long long tprev = 0, tacc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    const bool doProf = prof && crank == 0 && tid == 0;
+#define SOLVE_MARK(k) do { if (doProf) { const long long tn = clock64(); tacc[k] += tn - tprev; tprev = tn; } } while (0)
+    if (doProf) tprev = clock64();
     for (int jb = 0; jb < n; jb += LD_NB) {
         const int nb = min(LD_NB, n - jb), rows = n + 1 - jb;
         // (1) diagonal block
@@ -421,21 +456,28 @@ __global__ void __launch_bounds__(SOLVE_T) k_ba_solve(BADev D, double* __restric
             Pd[r][c] = (r < nb && c < nb && c <= r) ? __ldcg(A + (size_t)(jb + r) * n + jb + c) : 0.0;
         }
         __syncthreads();
+        SOLVE_MARK(0);
         {
+            // right-looking, ONE barrier per column: every thread reads the raw pivot column c (untouched during step c), forms the reciprocal of
+            // the pivot itself, updates its own 4 elements of columns > c; the owner of (r, c) files L[r][c] and (L d)[r][c] in PDd / Ld
             const int r = tid >> 3, cg4 = (tid & 7) * 4;   // thread owns elements (r, cg4 .. cg4+3)
             for (int c = 0; c < nb; c++) {
                 const double dc = Pd[c][c];
+                const double inv = 1.0 / dc;
                 if (tid == 0) { if (dc == 0.0 || !isfinite(dc)) fail = 1; dvec[c] = dc; }
-                if ((c >> 2) == (tid & 7) && r > c && r < nb) { const double v = Pd[r][c]; PDd[r][c] = v; Pd[r][c] = v / dc; }
-                __syncthreads();
                 if (r > c && r < nb) {
-                    const double ld = PDd[r][c];
+                    const double ld = Pd[r][c];   // (L d)[r][c]
+                    if ((c >> 2) == (tid & 7)) { PDd[r][c] = ld; Ld[r][c] = ld * inv; }
 #pragma unroll
-                    for (int k = 0; k < 4; k++) { const int c2 = cg4 + k; if (c2 > c && c2 <= r) Pd[r][c2] -= ld * Pd[c2][c]; }
+                    for (int k = 0; k < 4; k++) { const int c2 = cg4 + k; if (c2 > c && c2 <= r) Pd[r][c2] -= ld * (Pd[c2][c] * inv); }
                 }
                 __syncthreads();
             }
+            // Pd <- L (strict lower part), as the phases below expect
+            for (int i = tid; i < LD_NB * LD_NB; i += SOLVE_T) { const int rr2 = i / LD_NB, cc2 = i - rr2 * LD_NB; if (rr2 > cc2 && rr2 < nb) Pd[rr2][cc2] = Ld[rr2][cc2]; }
+            __syncthreads();
         }
+        SOLVE_MARK(1);
         if (fail) break;   // block-uniform and identical in every CTA of the cluster (same data)
         // (2) rows below the diagonal block (including the rhs row): a contiguous chunk of rows per CTA, one thread per row
         const int trR = rows - nb;
@@ -445,23 +487,26 @@ __global__ void __launch_bounds__(SOLVE_T) k_ba_solve(BADev D, double* __restric
             double x[LD_NB];
 #pragma unroll
             for (int c = 0; c < LD_NB; c++) x[c] = c < nb ? __ldcg(Arow + c) : 0.0;
+            // x[c] -= x[c2] * L[c][c2] for c2 = 0, 1, ... in that order per element (the order of the plain forward substitution), written
+            // right-looking so that the FMAs of one c2 step are independent of each other
 #pragma unroll
-            for (int c = 0; c < LD_NB; c++) {
-                if (c < nb) {
-                    double v = x[c];
+            for (int c2 = 0; c2 < LD_NB; c2++) {
+                if (c2 < nb) {
+                    const double v = x[c2];
 #pragma unroll
-                    for (int c2 = 0; c2 < c; c2++) v -= x[c2] * Pd[c][c2];
-                    x[c] = v;
-                    const double lv = v / dvec[c];
-                    __stcg(Arow + c, lv);
-                    __stcg(Lt + (size_t)c * ldp + rr, lv); __stcg(LDt + (size_t)c * ldp + rr, v);
+                    for (int c = c2 + 1; c < LD_NB; c++) if (c < nb) x[c] -= v * Pd[c][c2];
+                    const double lv = v / dvec[c2];
+                    __stcg(Arow + c2, lv);
+                    __stcg(Lt + (size_t)c2 * ldp + rr, lv); __stcg(LDt + (size_t)c2 * ldp + rr, v);
                 }
             }
         }
         // L of the diagonal block back into S (needed by the back substitution), by cluster rank 0
         if (crank == 0)
             for (int i = tid; i < nb * nb; i += SOLVE_T) { const int r = i / nb, c = i - r * nb; if (r > c) __stcg(A + (size_t)(jb + r) * n + jb + c, Pd[r][c]); }
+        SOLVE_MARK(2);
         cluster.sync();
+        SOLVE_MARK(3);
         // (3) trailing update A[i][k] -= sum_c (L d)[i][c] L[k][c], rows i include the rhs row, columns k < trC, k <= i
         const int trC = n - jb - nb;
         if (trC > 0) {
@@ -478,11 +523,17 @@ __global__ void __launch_bounds__(SOLVE_T) k_ba_solve(BADev D, double* __restric
                 __syncthreads();
                 pL = sL; pLD = sLD;
             }
+            SOLVE_MARK(4);
             const int tR = (trR + 3) >> 2, tC = (trC + 1) >> 1;
-            for (int i = crank * SOLVE_T + tid; i < tR * tC; i += C * SOLVE_T) {
-                const int br = i / tC, bc = i - br * tC;
+            // tile row br (4 rows) holds the tile columns bc with 2 bc <= 4 br + 3, i.e. bc <= 2 br + 1: 2 br + 2 tiles, br (br + 1) before it
+            const int nTiles = tR * (tR + 1);
+            for (int i = crank * SOLVE_T + tid; i < nTiles; i += C * SOLVE_T) {
+                int br = (int)((sqrt(4.0 * (double)i + 1.0) - 1.0) * 0.5);
+                while (br * (br + 1) > i) br--;
+                while ((br + 1) * (br + 2) <= i) br++;
+                const int bc = i - br * (br + 1);
+                if (bc >= tC) continue;
                 const int r0 = 4 * br, k0 = 2 * bc;
-                if (k0 > r0 + 3) continue;   // tile entirely above the diagonal
                 double acc[4][2] = {{0, 0}, {0, 0}, {0, 0}, {0, 0}};
                 if (stage) {
 #pragma unroll 8
@@ -513,7 +564,9 @@ __global__ void __launch_bounds__(SOLVE_T) k_ba_solve(BADev D, double* __restric
                 }
             }
         }
+        SOLVE_MARK(5);
         cluster.sync();
+        SOLVE_MARK(6);
     }
     if (fail) { if (crank == 0 && tid == 0) D.scal[3] = 1.0; return; }
     if (crank != 0) return;
@@ -525,12 +578,19 @@ __global__ void __launch_bounds__(SOLVE_T) k_ba_solve(BADev D, double* __restric
         const int j0 = max(je - LD_NB, 0), nb = je - j0;
         for (int i = tid; i < nb * nb; i += SOLVE_T) { const int r = i / nb, c = i - r * nb; Pd[r][c] = (r > c) ? __ldcg(A + (size_t)(j0 + r) * n + j0 + c) : 0.0; }
         __syncthreads();
-        if (tid < 32) {
-            for (int j = nb - 1; j >= 0; j--) {
-                const double xj = y[j0 + j];
-                if (tid < j) y[j0 + tid] -= Pd[j][tid] * xj;
-                __syncwarp();
+        if (tid < 32) {   // lane i owns y[j0 + i] and column i of the block: y_i -= L[j][i] x_j for j = nb-1 .. i+1
+            double yi = tid < nb ? y[j0 + tid] : 0.0;
+            double col[LD_NB];
+#pragma unroll
+            for (int j = 0; j < LD_NB; j++) col[j] = (j < nb && tid < j) ? Pd[j][tid] : 0.0;
+#pragma unroll
+            for (int j = LD_NB - 1; j >= 0; j--) {
+                if (j < nb) {
+                    const double xj = __shfl_sync(0xffffffffu, yi, j);
+                    yi -= col[j] * xj;   // col[j] == 0 for lanes >= j
+                }
             }
+            if (tid < nb) y[j0 + tid] = yi;
         }
         __syncthreads();
         // rows above: y[i] -= sum_{j in block} L[j][i] x_j   (rows of L are contiguous: coalesced over i; all loads of a thread are independent)
@@ -546,15 +606,18 @@ __global__ void __launch_bounds__(SOLVE_T) k_ba_solve(BADev D, double* __restric
         __syncthreads();
     }
     for (int i = tid; i < n; i += SOLVE_T) D.xp[i] = y[i];
+    SOLVE_MARK(7);
+    if (doProf) for (int k = 0; k < 8; k++) prof[k] += tacc[k];
+#undef SOLVE_MARK
 }
 
 // xl = Dinv (bl - Hpl^T xp)   (block_solver.hpp:461-481)
 __global__ void __launch_bounds__(128) k_ba_backsub(BADev D) {
-    const int l = blockIdx.x * blockDim.x + threadIdx.x;
-    if (l >= D.nMP) return;
-    if (!D.ptAct[l] || !owned(D, l)) { D.xl[3 * l] = 0; D.xl[3 * l + 1] = 0; D.xl[3 * l + 2] = 0; return; }
-    double cl[3] = {D.bl[3 * l], D.bl[3 * l + 1], D.bl[3 * l + 2]};
-    for (int a = D.lmStart[l]; a < D.lmStart[l + 1]; a++) {
+    const int l = (blockIdx.x * blockDim.x + threadIdx.x) / LM_LANES, sub = threadIdx.x % LM_LANES;
+    const bool in = l < D.nMP, act = in && D.ptAct[l] && owned(D, l);
+    double cl[3] = {0, 0, 0};
+    const int eBeg = act ? D.lmStart[l] : 0, eEnd = act ? D.lmStart[l + 1] : 0;
+    for (int a = eBeg + sub; a < eEnd; a += LM_LANES) {
         if (D.level[a] != 0) continue;
         const int p = D.poseIdx[D.eKF[a]];
         if (p < 0) continue;
@@ -563,8 +626,14 @@ __global__ void __launch_bounds__(128) k_ba_backsub(BADev D) {
 #pragma unroll
         for (int j = 0; j < 3; j++) { double s = 0;
 #pragma unroll
-            for (int i = 0; i < 6; i++) s += B[3 * i + j] * xq[i]; cl[j] -= s; }
+            for (int i = 0; i < 6; i++) s += B[3 * i + j] * xq[i]; cl[j] += s; }
     }
+#pragma unroll
+    for (int j = 0; j < 3; j++) { cl[j] += __shfl_xor_sync(0xffffffffu, cl[j], 1); cl[j] += __shfl_xor_sync(0xffffffffu, cl[j], 2); }
+    if (!in || sub) return;
+    if (!act) { D.xl[3 * l] = 0; D.xl[3 * l + 1] = 0; D.xl[3 * l + 2] = 0; return; }
+#pragma unroll
+    for (int j = 0; j < 3; j++) cl[j] = D.bl[3 * l + j] - cl[j];
     const double* Di = D.Dinv + 9 * (size_t)l;
 #pragma unroll
     for (int i = 0; i < 3; i++) D.xl[3 * l + i] = Di[3 * i] * cl[0] + Di[3 * i + 1] * cl[1] + Di[3 * i + 2] * cl[2];
@@ -807,6 +876,7 @@ struct BAHost {
     double* HppFull = nullptr;        // multi-GPU: all-reduced copy of the pose blocks for computeLambdaInit
     size_t xstride = 0;               // one-shot path: doubles between the two payload buffers of an exchange region
     int* d_xerr = nullptr;
+    long long* d_prof = nullptr;      // CSLAM_BA_PROFILE=1: clock64 per solver phase (debug)
     double lambda = -1, ni = 2; int nBad = 0; int iterations = 0, trials = 0;
     const volatile uint8_t* stop = nullptr;
     std::vector<int> h_eMP, h_eKF; int nActive = 0;
@@ -858,9 +928,9 @@ struct BAHost {
         return 0;
     }
     int build_system() {
-        k_ba_lin_points<<<grid(D.nMP, 128), 128, 0, o->stream>>>(D); o->launches++;
+        k_ba_lin_points<<<grid(D.nMP * LM_LANES, 128), 128, 0, o->stream>>>(D); o->launches++;
         tick(BK_LIN_POSES);
-        if (D.nQ > 0) { k_ba_lin_poses<<<D.nQ, 256, 0, o->stream>>>(D); o->launches++; }
+        if (D.nQ > 0) { k_ba_lin_poses<<<dim3(D.nQ, POSE_SPLIT), 256, 0, o->stream>>>(D); o->launches++; }
         CSLAM_CUDA(cudaGetLastError());
         return 0;
     }
@@ -931,10 +1001,10 @@ struct BAHost {
             cudaLaunchAttribute at[1];
             at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = o->clusterSize; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
             cfg.attrs = at; cfg.numAttrs = 1;
-            CSLAM_CUDA(cudaLaunchKernelEx(&cfg, k_ba_solve, R, Lt, LDt, ldp, stage)); o->launches++;
+            CSLAM_CUDA(cudaLaunchKernelEx(&cfg, k_ba_solve, R, Lt, LDt, ldp, stage, d_prof)); o->launches++;
         }
         tick(BK_BACKSUB);
-        k_ba_backsub<<<grid(D.nMP, 128), 128, 0, o->stream>>>(D); o->launches++;
+        k_ba_backsub<<<grid(D.nMP * LM_LANES, 128), 128, 0, o->stream>>>(D); o->launches++;
         tick(BK_UPDATE);
         k_ba_update<<<grid(std::max(D.nKF, D.nMP)), 256, 0, o->stream>>>(D); o->launches++;
         tick(BK_ERRORS);
@@ -1127,10 +1197,11 @@ extern "C" int cslam_local_ba(cslam_optimizer* o, cslam_ba_problem* p, const vol
         (rc = dalloc(o, &D.bp, (size_t)std::max(nQ, 1) * 6)) || (rc = dalloc(o, &D.Hll, (size_t)nMP * 9)) || (rc = dalloc(o, &D.bl, (size_t)nMP * 3)) ||
         (rc = dalloc(o, &D.Hpl, (size_t)nE * 18)) || (rc = dalloc(o, &D.Dinv, (size_t)nMP * 9)) || (rc = dalloc(o, &D.db, (size_t)nMP * 3)) ||
         (rc = dalloc(o, &H.red, payloadMax)) || (rc = dalloc(o, &D.xp, std::max(nmax, 1), true)) || (rc = dalloc(o, &D.xl, (size_t)nMP * 3, true)) ||
-        (rc = dalloc(o, &D.scal, 8, true)) || (rc = dalloc(o, &D.part, maxBlocks)) || (rc = dalloc(o, &D.ticket, 4, true)) ||
+        (rc = dalloc(o, &D.scal, 8, true)) || (rc = dalloc(o, &D.part, maxBlocks)) || (rc = dalloc(o, &D.ticket, 4, true)) || (rc = dalloc(o, &D.posePart, (size_t)std::max(nQ, 1) * POSE_SPLIT * 27)) || (rc = dalloc(o, &D.poseTicket, std::max(nQ, 1), true)) ||
         (rc = dalloc(o, &H.Lt, (size_t)LD_NB * H.ldp)) || (rc = dalloc(o, &H.LDt, (size_t)LD_NB * H.ldp)) || (rc = dalloc(o, &pairCnt, (size_t)nQ * nQ + 1)) ||
         (rc = dalloc(o, &H.d_xerr, 1, true))) return rc;
     D.poseIdx = H.d_poseIdx; D.ptAct = H.d_ptAct;
+    if (getenv("CSLAM_BA_PROFILE")) { if ((rc = dalloc(o, &H.d_prof, 8, true))) return rc; }
     // ---- multi-GPU exchange path
     if (o->nranks > 1) {
         if (!getenv("CSLAM_BA_NCCL_ONLY") && (!o->oneShot || o->xchgBytes < payloadMax * 8)) {
@@ -1167,6 +1238,11 @@ extern "C" int cslam_local_ba(cslam_optimizer* o, cslam_ba_problem* p, const vol
     }
     if ((rc = H.classify(flags))) return rc;
     H.drop_graph();
+    if (H.d_prof) {
+        long long hp[8]; cudaMemcpyAsync(hp, H.d_prof, sizeof(hp), cudaMemcpyDeviceToHost, o->stream); cudaStreamSynchronize(o->stream);
+        static const char* nm[8] = {"load diag", "factor diag", "trsm", "cluster sync 1", "stage panel", "trailing update", "cluster sync 2", "back substitution"};
+        for (int k = 0; k < 8; k++) std::fprintf(stderr, "[k_ba_solve] %-18s %10.1f kclk total, %7.2f us per trial\n", nm[k], hp[k] / 1e3, hp[k] / 1.9e3 / std::max(H.trials, 1));
+    }
     // ---- write back (src/Optimizer.cpp:432-450): float32 poses / points; with landmark sharding every rank holds its own points
     if (o->nranks > 1) {
         k_ba_mask_points<<<H.grid(nMP), 256, 0, o->stream>>>(D); o->launches++;
