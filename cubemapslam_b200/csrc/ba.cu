@@ -418,28 +418,41 @@ __global__ void __launch_bounds__(SCHUR_T) k_ba_schur(BADev D, int addLambda) {
 // ---------------------------------------------------------------------------------------------- reduced camera system solve
 // Blocked right-looking LDL^T (no pivoting; LinearSolverEigen's SimplicialLDLT has none either) of the n x n system in ONE thread-block
 // cluster. The right-hand side g sits right behind S, i.e. it is row n of an (n+1) x n matrix: carrying it through the factorisation
-// as one more row performs the forward substitution (row n of L = D^-1 L^-1 g). Per panel of NB columns:
-//   (1) every CTA factors the NB x NB diagonal block redundantly (shared memory, all 256 threads, two barriers per column);
-//   (2) the rows below are NB-step forward substitutions, one thread per row, rows dealt round-robin to the CTAs of the cluster;
-//       L goes back into S (row-major, for the back substitution) and L, L*d go to the transposed panel buffers Lt / LDt;
-//   (3) cluster barrier; trailing update with 4x2 register tiles, tiles dealt over all threads of the cluster, panel values
-//       streamed from L2 (coalesced, L1 bypassed); cluster barrier.
-// scal[3] = 1 on a zero / non-finite pivot (LinearSolverEigen's failure): the LM trial is rejected.
+// as one more row performs the forward substitution (row n of L = D^-1 L^-1 g).
+//
+// Everything here is LATENCY bound (n ~ 300: 9 MFLOP; measured on B200, tools/ubench_fp64.cu: DFMA 8 clk, fp64 divide 127 clk, shared
+// load 29 clk, __syncthreads 38 clk, L2 load 375 clk, cluster barrier 420 clk), so every phase is written to keep its dependent chain short
+// and to have all of a thread's L2 loads in flight together. Per panel of NB = 32 columns:
+//   (1) every CTA factors the NB x NB diagonal block redundantly: thread (r, g) keeps elements (r, 4g..4g+3) in registers, the pivot column is
+//       published through a double-buffered shared column -> one barrier per column; 1 / pivot = rcp.approx + 2 Newton steps (~55 clk);
+//   (2) the rows below are forward substitutions, FOUR lanes per row (8 columns each, 8 x 8 blocks: the owner finishes its block, its 8
+//       values go to the other lanes by shuffle), a contiguous chunk of rows per CTA; L goes back into S (row-major, for the back
+//       substitution) and L, L d go to the transposed panel buffers Lt / LDt;
+//   (3) cluster barrier; every CTA copies both panels to shared memory (16-byte L2 loads, 4 in flight per thread); trailing update with
+//       4 x 2 register tiles enumerated over the lower triangle only and dealt over all threads of the cluster; cluster barrier.
+// Back substitution by cluster rank 0: per block of NB columns a warp-level triangular solve (shuffles) whose latency covers the L2 loads
+// of the rows above. scal[3] = 1 on a zero / non-finite pivot (LinearSolverEigen's failure): the LM trial is rejected.
 static const int LD_NB = 32;
 static const int SOLVE_T = 256;
 
-// Panel staging: when both transposed panels (L and L*d, NB x rows each) fit in shared memory every CTA copies them there once per panel with
-// coalesced 16-byte L2 loads and the 4x2 register tiles of the trailing update read shared memory; otherwise the tiles stream from L2.
+// 1 / d to within an ulp: MUFU.RCP64H seed (~20 bits) and two Newton steps, instead of the ~127 clk IEEE divide on the critical path
+__device__ __forceinline__ double fast_rcp(double d) {
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(d));
+    r = fma(r, fma(-d, r, 1.0), r);
+    r = fma(r, fma(-d, r, 1.0), r);
+    return r;
+}
+
 __global__ void __launch_bounds__(SOLVE_T) k_ba_solve(BADev D, double* __restrict__ Lt, double* __restrict__ LDt, int ldp, int stage, long long* prof) {
     extern __shared__ double dsm[];                 // [stage ? 2 * NB * ldp : 0] panels, then y[n] for the back substitution
-    __shared__ double Pd[LD_NB][LD_NB + 1];         // diagonal block: L below the diagonal after (1)
-    __shared__ double PDd[LD_NB][LD_NB + 1];        // L * d
-    __shared__ double Ld[LD_NB][LD_NB + 1];         // L of the diagonal block while Pd still holds the working columns
-    __shared__ double dvec[LD_NB];
+    __shared__ double Pd[LD_NB][LD_NB + 1];         // L of the diagonal block (strictly lower part)
+    __shared__ double colbuf[2][LD_NB];             // the pivot column of the current / next step
+    __shared__ double dinvv[LD_NB];
     __shared__ int fail;
     cg::cluster_group cluster = cg::this_cluster();
     const int C = cluster.num_blocks(), crank = cluster.block_rank();
-    const int n = D.n, tid = threadIdx.x;
+    const int n = D.n, tid = threadIdx.x, lane = tid & 31;
     double* A = D.S;
     double* sL = dsm; double* sLD = dsm + (size_t)LD_NB * ldp;
     if (tid == 0) fail = 0;
@@ -450,117 +463,155 @@ __global__ void __launch_bounds__(SOLVE_T) k_ba_solve(BADev D, double* __restric
     if (doProf) tprev = clock64();
     for (int jb = 0; jb < n; jb += LD_NB) {
         const int nb = min(LD_NB, n - jb), rows = n + 1 - jb;
-        // (1) diagonal block
-        for (int i = tid; i < LD_NB * LD_NB; i += SOLVE_T) {
-            const int r = i / LD_NB, c = i - r * LD_NB;
-            Pd[r][c] = (r < nb && c < nb && c <= r) ? __ldcg(A + (size_t)(jb + r) * n + jb + c) : 0.0;
-        }
+        // (1) diagonal block: thread (r, g) owns (r, 4g .. 4g+3)
+        const int r = tid >> 3, g4 = (tid & 7) * 4;
+        double a[4];
+#pragma unroll
+        for (int k = 0; k < 4; k++) { const int c = g4 + k; a[k] = (r < nb && c <= r) ? __ldcg(A + (size_t)(jb + r) * n + jb + c) : 0.0; }
+        if (g4 == 0) colbuf[0][r] = a[0];
         __syncthreads();
         SOLVE_MARK(0);
-        {
-            // right-looking, ONE barrier per column: every thread reads the raw pivot column c (untouched during step c), forms the reciprocal of
-            // the pivot itself, updates its own 4 elements of columns > c; the owner of (r, c) files L[r][c] and (L d)[r][c] in PDd / Ld
-            const int r = tid >> 3, cg4 = (tid & 7) * 4;   // thread owns elements (r, cg4 .. cg4+3)
-            for (int c = 0; c < nb; c++) {
-                const double dc = Pd[c][c];
-                const double inv = 1.0 / dc;
-                if (tid == 0) { if (dc == 0.0 || !isfinite(dc)) fail = 1; dvec[c] = dc; }
-                if (r > c && r < nb) {
-                    const double ld = Pd[r][c];   // (L d)[r][c]
-                    if ((c >> 2) == (tid & 7)) { PDd[r][c] = ld; Ld[r][c] = ld * inv; }
 #pragma unroll
-                    for (int k = 0; k < 4; k++) { const int c2 = cg4 + k; if (c2 > c && c2 <= r) Pd[r][c2] -= ld * (Pd[c2][c] * inv); }
+        for (int c = 0; c < LD_NB; c++) {
+            if (c < nb) {   // block-uniform
+                const double* col = colbuf[c & 1];
+                const double dc = col[c], ld = col[r];
+                double l4[4];
+#pragma unroll
+                for (int k = 0; k < 4; k++) l4[k] = col[g4 + k];
+                const double inv = fast_rcp(dc);
+                if (tid == 0) { if (dc == 0.0 || !isfinite(dc)) fail = 1; dinvv[c] = inv; }
+                if (r > c) {
+#pragma unroll
+                    for (int k = 0; k < 4; k++) { const int c2 = g4 + k; if (c2 > c && c2 <= r) a[k] -= ld * (l4[k] * inv); }
+                    if ((c >> 2) == (tid & 7)) Pd[r][c] = ld * inv;
                 }
+                if (c + 1 < nb && ((c + 1) >> 2) == (tid & 7)) colbuf[(c + 1) & 1][r] = a[(c + 1) & 3];
                 __syncthreads();
             }
-            // Pd <- L (strict lower part), as the phases below expect
-            for (int i = tid; i < LD_NB * LD_NB; i += SOLVE_T) { const int rr2 = i / LD_NB, cc2 = i - rr2 * LD_NB; if (rr2 > cc2 && rr2 < nb) Pd[rr2][cc2] = Ld[rr2][cc2]; }
-            __syncthreads();
         }
         SOLVE_MARK(1);
         if (fail) break;   // block-uniform and identical in every CTA of the cluster (same data)
-        // (2) rows below the diagonal block (including the rhs row): a contiguous chunk of rows per CTA, one thread per row
+        // (2) rows below the diagonal block (including the rhs row): a contiguous chunk of rows per CTA, 4 lanes per row, 8 columns per lane.
+        // Per element the subtractions run over c2 = 0, 1, ... in the order of the plain forward substitution.
         const int trR = rows - nb;
         const int chunk = (trR + C - 1) / C, r0c = crank * chunk, r1c = min(r0c + chunk, trR);
-        for (int rr = r0c + tid; rr < r1c; rr += SOLVE_T) {
-            double* Arow = A + (size_t)(jb + nb + rr) * n + jb;
-            double x[LD_NB];
+        {
+            const int j = tid & 3, slot = tid >> 2;
+            for (int base = r0c; base < r1c; base += SOLVE_T / 4) {   // block-uniform trip count
+                const int rr = base + slot;
+                const bool valid = rr < r1c;
+                double* Arow = A + (size_t)(jb + nb + (valid ? rr : r0c)) * n + jb + 8 * j;
+                double x[8];
 #pragma unroll
-            for (int c = 0; c < LD_NB; c++) x[c] = c < nb ? __ldcg(Arow + c) : 0.0;
-            // x[c] -= x[c2] * L[c][c2] for c2 = 0, 1, ... in that order per element (the order of the plain forward substitution), written
-            // right-looking so that the FMAs of one c2 step are independent of each other
+                for (int k = 0; k < 8; k++) x[k] = (valid && 8 * j + k < nb) ? __ldcg(Arow + k) : 0.0;
 #pragma unroll
-            for (int c2 = 0; c2 < LD_NB; c2++) {
-                if (c2 < nb) {
-                    const double v = x[c2];
+                for (int b = 0; b < 4; b++) {
+                    if (8 * b < nb) {   // block-uniform
+                        if (j == b) {
 #pragma unroll
-                    for (int c = c2 + 1; c < LD_NB; c++) if (c < nb) x[c] -= v * Pd[c][c2];
-                    const double lv = v / dvec[c2];
-                    __stcg(Arow + c2, lv);
-                    __stcg(Lt + (size_t)c2 * ldp + rr, lv); __stcg(LDt + (size_t)c2 * ldp + rr, v);
+                            for (int k2 = 0; k2 < 8; k2++)
+#pragma unroll
+                                for (int k = k2 + 1; k < 8; k++) x[k] -= x[k2] * Pd[8 * b + k][8 * b + k2];
+                        }
+                        double v[8];
+#pragma unroll
+                        for (int k2 = 0; k2 < 8; k2++) v[k2] = __shfl_sync(0xffffffffu, x[k2], (lane & ~3) | b);
+                        if (j > b) {
+#pragma unroll
+                            for (int k2 = 0; k2 < 8; k2++)
+#pragma unroll
+                                for (int k = 0; k < 8; k++) x[k] -= v[k2] * Pd[8 * j + k][8 * b + k2];
+                        }
+                    }
+                }
+                if (valid) {
+#pragma unroll
+                    for (int k = 0; k < 8; k++) {
+                        const int c = 8 * j + k;
+                        if (c < nb) {
+                            const double lv = x[k] * dinvv[c];
+                            __stcg(Arow + k, lv);
+                            __stcg(Lt + (size_t)c * ldp + rr, lv); __stcg(LDt + (size_t)c * ldp + rr, x[k]);
+                        }
+                    }
                 }
             }
         }
         // L of the diagonal block back into S (needed by the back substitution), by cluster rank 0
         if (crank == 0)
-            for (int i = tid; i < nb * nb; i += SOLVE_T) { const int r = i / nb, c = i - r * nb; if (r > c) __stcg(A + (size_t)(jb + r) * n + jb + c, Pd[r][c]); }
+            for (int i = tid; i < nb * nb; i += SOLVE_T) { const int rr = i / nb, c = i - rr * nb; if (rr > c) __stcg(A + (size_t)(jb + rr) * n + jb + c, Pd[rr][c]); }
         SOLVE_MARK(2);
         cluster.sync();
         SOLVE_MARK(3);
         // (3) trailing update A[i][k] -= sum_c (L d)[i][c] L[k][c], rows i include the rhs row, columns k < trC, k <= i
         const int trC = n - jb - nb;
         if (trC > 0) {
-            const double* pL = Lt; const double* pLD = LDt;
             if (stage) {
-                const int w2 = (trR + 1) >> 1;   // double2 words per panel row
-                for (int i = tid; i < LD_NB * w2; i += SOLVE_T) {
-                    const int c = i / w2, q = i - c * w2;
-                    if (c < nb) {
-                        reinterpret_cast<double2*>(sL + (size_t)c * ldp)[q] = __ldcg(reinterpret_cast<const double2*>(Lt + (size_t)c * ldp) + q);
-                        reinterpret_cast<double2*>(sLD + (size_t)c * ldp)[q] = __ldcg(reinterpret_cast<const double2*>(LDt + (size_t)c * ldp) + q);
+                const int w2 = (trR + 1) >> 1, tot = nb * w2;   // double2 words per panel row / in a panel
+                for (int i0 = tid; i0 < tot; i0 += 4 * SOLVE_T) {
+                    double2 vl[4], vd[4]; int off[4];
+#pragma unroll
+                    for (int u = 0; u < 4; u++) {
+                        const int i = i0 + u * SOLVE_T;
+                        if (i < tot) {
+                            const int c = i / w2, q = i - c * w2;
+                            off[u] = c * (ldp >> 1) + q;
+                            vl[u] = __ldcg(reinterpret_cast<const double2*>(Lt) + off[u]);
+                            vd[u] = __ldcg(reinterpret_cast<const double2*>(LDt) + off[u]);
+                        } else off[u] = -1;
                     }
+#pragma unroll
+                    for (int u = 0; u < 4; u++) if (off[u] >= 0) { reinterpret_cast<double2*>(sL)[off[u]] = vl[u]; reinterpret_cast<double2*>(sLD)[off[u]] = vd[u]; }
                 }
                 __syncthreads();
-                pL = sL; pLD = sLD;
             }
             SOLVE_MARK(4);
             const int tR = (trR + 3) >> 2, tC = (trC + 1) >> 1;
             // tile row br (4 rows) holds the tile columns bc with 2 bc <= 4 br + 3, i.e. bc <= 2 br + 1: 2 br + 2 tiles, br (br + 1) before it
             const int nTiles = tR * (tR + 1);
             for (int i = crank * SOLVE_T + tid; i < nTiles; i += C * SOLVE_T) {
-                int br = (int)((sqrt(4.0 * (double)i + 1.0) - 1.0) * 0.5);
+                int br = (int)((sqrtf(4.0f * (float)i + 1.0f) - 1.0f) * 0.5f);
                 while (br * (br + 1) > i) br--;
                 while ((br + 1) * (br + 2) <= i) br++;
                 const int bc = i - br * (br + 1);
                 if (bc >= tC) continue;
                 const int r0 = 4 * br, k0 = 2 * bc;
+                // destination values first: their L2 latency runs under the product loop
+                double dv[4][2]; bool ok[4][2];
+#pragma unroll
+                for (int q = 0; q < 4; q++) {
+                    const int rr = r0 + q;
+                    const double* dst = A + (size_t)(jb + nb + min(rr, trR - 1)) * n + jb + nb;
+                    ok[q][0] = rr < trR && k0 <= rr && k0 < trC; ok[q][1] = rr < trR && k0 + 1 <= rr && k0 + 1 < trC;
+                    dv[q][0] = ok[q][0] ? __ldcg(dst + k0) : 0.0; dv[q][1] = ok[q][1] ? __ldcg(dst + k0 + 1) : 0.0;
+                }
                 double acc[4][2] = {{0, 0}, {0, 0}, {0, 0}, {0, 0}};
                 if (stage) {
+                    const double2* qL = reinterpret_cast<const double2*>(sL + k0);
+                    const double2* qD = reinterpret_cast<const double2*>(sLD + r0);
+                    const int st = ldp >> 1;
 #pragma unroll 8
                     for (int c = 0; c < nb; c++) {
-                        const double2 bv = *reinterpret_cast<const double2*>(pL + (size_t)c * ldp + k0);
-                        const double2 a01 = *reinterpret_cast<const double2*>(pLD + (size_t)c * ldp + r0);
-                        const double2 a23 = *reinterpret_cast<const double2*>(pLD + (size_t)c * ldp + r0 + 2);
+                        const double2 bv = qL[c * st], a01 = qD[c * st], a23 = qD[c * st + 1];
                         acc[0][0] += a01.x * bv.x; acc[0][1] += a01.x * bv.y; acc[1][0] += a01.y * bv.x; acc[1][1] += a01.y * bv.y;
                         acc[2][0] += a23.x * bv.x; acc[2][1] += a23.x * bv.y; acc[3][0] += a23.y * bv.x; acc[3][1] += a23.y * bv.y;
                     }
                 } else {
 #pragma unroll 8
                     for (int c = 0; c < nb; c++) {
-                        const double2 bv = __ldcg(reinterpret_cast<const double2*>(pL + (size_t)c * ldp + k0));
-                        const double2 a01 = __ldcg(reinterpret_cast<const double2*>(pLD + (size_t)c * ldp + r0));
-                        const double2 a23 = __ldcg(reinterpret_cast<const double2*>(pLD + (size_t)c * ldp + r0 + 2));
+                        const double2 bv = __ldcg(reinterpret_cast<const double2*>(Lt + (size_t)c * ldp + k0));
+                        const double2 a01 = __ldcg(reinterpret_cast<const double2*>(LDt + (size_t)c * ldp + r0));
+                        const double2 a23 = __ldcg(reinterpret_cast<const double2*>(LDt + (size_t)c * ldp + r0 + 2));
                         acc[0][0] += a01.x * bv.x; acc[0][1] += a01.x * bv.y; acc[1][0] += a01.y * bv.x; acc[1][1] += a01.y * bv.y;
                         acc[2][0] += a23.x * bv.x; acc[2][1] += a23.x * bv.y; acc[3][0] += a23.y * bv.x; acc[3][1] += a23.y * bv.y;
                     }
                 }
 #pragma unroll
-                for (int a = 0; a < 4; a++) {
-                    const int r = r0 + a;
-                    if (r >= trR) break;
-                    double* dst = A + (size_t)(jb + nb + r) * n + jb + nb;
-                    if (k0 <= r && k0 < trC) __stcg(dst + k0, __ldcg(dst + k0) - acc[a][0]);
-                    if (k0 + 1 <= r && k0 + 1 < trC) __stcg(dst + k0 + 1, __ldcg(dst + k0 + 1) - acc[a][1]);
+                for (int q = 0; q < 4; q++) {
+                    double* dst = A + (size_t)(jb + nb + min(r0 + q, trR - 1)) * n + jb + nb;
+                    if (ok[q][0]) __stcg(dst + k0, dv[q][0] - acc[q][0]);
+                    if (ok[q][1]) __stcg(dst + k0 + 1, dv[q][1] - acc[q][1]);
                 }
             }
         }
@@ -576,13 +627,19 @@ __global__ void __launch_bounds__(SOLVE_T) k_ba_solve(BADev D, double* __restric
     __syncthreads();
     for (int je = n; je > 0; je -= LD_NB) {
         const int j0 = max(je - LD_NB, 0), nb = je - j0;
-        for (int i = tid; i < nb * nb; i += SOLVE_T) { const int r = i / nb, c = i - r * nb; Pd[r][c] = (r > c) ? __ldcg(A + (size_t)(j0 + r) * n + j0 + c) : 0.0; }
-        __syncthreads();
+        // rows above the block: L[j0 + j][i] for this thread's rows i (independent of the block solve -> the loads fly under it)
+        double v0[LD_NB], v1[LD_NB];
+        const int i0 = tid, i1 = tid + SOLVE_T;   // n <= 2 * SOLVE_T is the staged regime; larger systems loop below
+#pragma unroll
+        for (int j = 0; j < LD_NB; j++) {
+            v0[j] = (j < nb && i0 < j0) ? __ldcg(A + (size_t)(j0 + j) * n + i0) : 0.0;
+            v1[j] = (j < nb && i1 < j0) ? __ldcg(A + (size_t)(j0 + j) * n + i1) : 0.0;
+        }
         if (tid < 32) {   // lane i owns y[j0 + i] and column i of the block: y_i -= L[j][i] x_j for j = nb-1 .. i+1
             double yi = tid < nb ? y[j0 + tid] : 0.0;
             double col[LD_NB];
 #pragma unroll
-            for (int j = 0; j < LD_NB; j++) col[j] = (j < nb && tid < j) ? Pd[j][tid] : 0.0;
+            for (int j = 0; j < LD_NB; j++) col[j] = (j < nb && tid < j) ? __ldcg(A + (size_t)(j0 + j) * n + j0 + tid) : 0.0;
 #pragma unroll
             for (int j = LD_NB - 1; j >= 0; j--) {
                 if (j < nb) {
@@ -593,14 +650,16 @@ __global__ void __launch_bounds__(SOLVE_T) k_ba_solve(BADev D, double* __restric
             if (tid < nb) y[j0 + tid] = yi;
         }
         __syncthreads();
-        // rows above: y[i] -= sum_{j in block} L[j][i] x_j   (rows of L are contiguous: coalesced over i; all loads of a thread are independent)
-        for (int i = tid; i < j0; i += SOLVE_T) {
-            double v[LD_NB];
+        {
+            double s0 = 0, s1 = 0;
 #pragma unroll
-            for (int j = 0; j < LD_NB; j++) v[j] = j < nb ? __ldcg(A + (size_t)(j0 + j) * n + i) : 0.0;
+            for (int j = 0; j < LD_NB; j++) if (j < nb) { const double xj = y[j0 + j]; s0 += v0[j] * xj; s1 += v1[j] * xj; }
+            if (i0 < j0) y[i0] -= s0;
+            if (i1 < j0) y[i1] -= s1;
+        }
+        for (int i = tid + 2 * SOLVE_T; i < j0; i += SOLVE_T) {
             double sacc = 0;
-#pragma unroll
-            for (int j = 0; j < LD_NB; j++) if (j < nb) sacc += v[j] * y[j0 + j];
+            for (int j = 0; j < nb; j++) sacc += __ldcg(A + (size_t)(j0 + j) * n + i) * y[j0 + j];
             y[i] -= sacc;
         }
         __syncthreads();
