@@ -25,6 +25,7 @@
 #include <dlfcn.h>
 #include <algorithm>
 #include <cfloat>
+#include <chrono>
 #include <cstring>
 #include <vector>
 #include "optimizer.cuh"
@@ -56,6 +57,8 @@ struct BADev {
     int robust; double delta, dsqr;
     int rank, nranks;                // landmark l is owned by rank l % nranks
 };
+
+static const int DINV_LD = 10;   // doubles per landmark in Dinv: 9 + 1 pad, so that every block is 16-byte aligned for the 128-bit loads of k_ba_schur
 
 __device__ __forceinline__ bool owned(const BADev& D, int l) { return D.nranks == 1 || (l % D.nranks) == D.rank; }
 
@@ -238,7 +241,7 @@ __global__ void __launch_bounds__(256) k_ba_dinv(BADev D) {
     const double lambda = D.scal[4];
     const int l = blockIdx.x * blockDim.x + threadIdx.x;
     if (l >= D.nMP || !owned(D, l)) return;
-    double* Dv = D.Dinv + 9 * (size_t)l;
+    double* Dv = D.Dinv + DINV_LD * (size_t)l;
     if (!D.ptAct[l]) {
 #pragma unroll
         for (int i = 0; i < 9; i++) Dv[i] = 0.0;
@@ -361,14 +364,17 @@ __global__ void __launch_bounds__(SCHUR_T) k_ba_schur(BADev D, int addLambda) {
         const int2 tp = D.tuples[t];
         const int l = D.eMP[tp.x];
         if (!owned(D, l)) continue;
-        const double* B1 = D.Hpl + 18 * (size_t)tp.x + 9 * h;
-        const double* B2 = D.Hpl + 18 * (size_t)tp.y;
-        const double* Di = D.Dinv + 9 * (size_t)l;
-        double b1[9], di[9], b2[18];
+        // 19 128-bit loads per thread: every lane reads a different block, so the L1 wavefront count per byte is what bounds this kernel
+        const double2* B1v = reinterpret_cast<const double2*>(D.Hpl + 18 * (size_t)tp.x) + 4 * h;   // doubles 8h .. 8h+9: rows 3h..3h+2 are w[h .. h+8]
+        const double2* B2v = reinterpret_cast<const double2*>(D.Hpl + 18 * (size_t)tp.y);
+        const double2* Div = reinterpret_cast<const double2*>(D.Dinv + DINV_LD * (size_t)l);
+        double w[10], di[10], b2[18], b1[9];
 #pragma unroll
-        for (int i = 0; i < 9; i++) { b1[i] = B1[i]; di[i] = Di[i]; }
+        for (int i = 0; i < 5; i++) { const double2 v = B1v[i]; w[2 * i] = v.x; w[2 * i + 1] = v.y; const double2 u = Div[i]; di[2 * i] = u.x; di[2 * i + 1] = u.y; }
 #pragma unroll
-        for (int i = 0; i < 18; i++) b2[i] = B2[i];
+        for (int i = 0; i < 9; i++) { const double2 v = B2v[i]; b2[2 * i] = v.x; b2[2 * i + 1] = v.y; }
+#pragma unroll
+        for (int i = 0; i < 9; i++) b1[i] = h ? w[i + 1] : w[i];
 #pragma unroll
         for (int i = 0; i < 3; i++) {
             const double t0 = b1[3 * i] * di[0] + b1[3 * i + 1] * di[3] + b1[3 * i + 2] * di[6];
@@ -424,14 +430,15 @@ __global__ void __launch_bounds__(SCHUR_T) k_ba_schur(BADev D, int addLambda) {
 // load 29 clk, __syncthreads 38 clk, L2 load 375 clk, cluster barrier 420 clk), so every phase is written to keep its dependent chain short
 // and to have all of a thread's L2 loads in flight together. Per panel of NB = 32 columns:
 //   (1) every CTA factors the NB x NB diagonal block redundantly: thread (r, g) keeps elements (r, 4g..4g+3) in registers, the pivot column is
-//       published through a double-buffered shared column -> one barrier per column; 1 / pivot = rcp.approx + 2 Newton steps (~55 clk);
-//   (2) the rows below are forward substitutions, FOUR lanes per row (8 columns each, 8 x 8 blocks: the owner finishes its block, its 8
-//       values go to the other lanes by shuffle), a contiguous chunk of rows per CTA; L goes back into S (row-major, for the back
-//       substitution) and L, L d go to the transposed panel buffers Lt / LDt;
+//       published through a double-buffered shared column -> one barrier per column; 1 / pivot = rcp.approx + 2 Newton steps (~55 clk).
+//       Then M = (unit lower factor)^-1: each warp solves L m = e_k for 4 columns, lane = row, pivot entries by shuffle (no barrier);
+//   (2) the rows below become a product instead of forward substitutions: X = A_rows M^T, L = X / d; FOUR lanes per row, lane j forms
+//       the columns j, j+4, ... from the row held in registers (no dependent chain, no shuffles), a contiguous chunk of rows per CTA;
+//       L goes back into S (row-major, for the back substitution) and L, L d go to the transposed panel buffers Lt / LDt;
 //   (3) cluster barrier; every CTA copies both panels to shared memory (16-byte L2 loads, 4 in flight per thread); trailing update with
 //       4 x 2 register tiles enumerated over the lower triangle only and dealt over all threads of the cluster; cluster barrier.
-// Back substitution by cluster rank 0: per block of NB columns a warp-level triangular solve (shuffles) whose latency covers the L2 loads
-// of the rows above. scal[3] = 1 on a zero / non-finite pivot (LinearSolverEigen's failure): the LM trial is rejected.
+// Back substitution by cluster rank 0, panel by panel from the bottom: x_b = M_b^T y_b (one warp, 32 independent products per lane; M_b
+// was parked in L2 scratch by (2)) instead of a 32-step triangular solve, then the rows above take y -= L_b^T x_b. scal[3] = 1 on a zero / non-finite pivot (LinearSolverEigen's failure): the LM trial is rejected.
 static const int LD_NB = 32;
 static const int SOLVE_T = 256;
 
@@ -444,15 +451,16 @@ __device__ __forceinline__ double fast_rcp(double d) {
     return r;
 }
 
-__global__ void __launch_bounds__(SOLVE_T) k_ba_solve(BADev D, double* __restrict__ Lt, double* __restrict__ LDt, int ldp, int stage, long long* prof) {
+__global__ void __launch_bounds__(SOLVE_T) k_ba_solve(BADev D, double* __restrict__ Lt, double* __restrict__ LDt, double* __restrict__ Mg, int ldp, int stage, long long* prof) {
     extern __shared__ double dsm[];                 // [stage ? 2 * NB * ldp : 0] panels, then y[n] for the back substitution
     __shared__ double Pd[LD_NB][LD_NB + 1];         // L of the diagonal block (strictly lower part)
+    __shared__ double Msm[LD_NB][LD_NB + 1];        // M = L^-1 of the diagonal block (zeros above the diagonal)
     __shared__ double colbuf[2][LD_NB];             // the pivot column of the current / next step
     __shared__ double dinvv[LD_NB];
     __shared__ int fail;
     cg::cluster_group cluster = cg::this_cluster();
     const int C = cluster.num_blocks(), crank = cluster.block_rank();
-    const int n = D.n, tid = threadIdx.x, lane = tid & 31;
+    const int n = D.n, tid = threadIdx.x;
     double* A = D.S;
     double* sL = dsm; double* sLD = dsm + (size_t)LD_NB * ldp;
     if (tid == 0) fail = 0;
@@ -480,16 +488,41 @@ __global__ void __launch_bounds__(SOLVE_T) k_ba_solve(BADev D, double* __restric
 #pragma unroll
                 for (int k = 0; k < 4; k++) l4[k] = col[g4 + k];
                 const double inv = fast_rcp(dc);
-                if (tid == 0) { if (dc == 0.0 || !isfinite(dc)) fail = 1; dinvv[c] = inv; }
+                if (tid == 0) dinvv[c] = inv;
                 if (r > c) {
 #pragma unroll
                     for (int k = 0; k < 4; k++) { const int c2 = g4 + k; if (c2 > c && c2 <= r) a[k] -= ld * (l4[k] * inv); }
-                    if ((c >> 2) == (tid & 7)) Pd[r][c] = ld * inv;
                 }
+                if ((c >> 2) == (tid & 7)) Pd[r][c] = r > c ? ld * inv : 0.0;
                 if (c + 1 < nb && ((c + 1) >> 2) == (tid & 7)) colbuf[(c + 1) & 1][r] = a[(c + 1) & 3];
                 __syncthreads();
             }
         }
+        // M = L^-1: warp w solves L m = e_k for the columns k = w, w+8, w+16, w+24 (lane = row; right-looking, the pivot entry travels by shuffle,
+        // no block barrier inside). Columns >= nb of a short last panel stay unit vectors and are never used.
+        {
+            const int w = tid >> 5, ln = tid & 31;
+            double mk[4], lrow[LD_NB];
+#pragma unroll
+            for (int c = 0; c < LD_NB; c++) lrow[c] = (c < nb && ln < nb && ln > c) ? Pd[ln][c] : 0.0;
+#pragma unroll
+            for (int q = 0; q < 4; q++) mk[q] = ln == w + 8 * q ? 1.0 : 0.0;
+#pragma unroll
+            for (int c = 0; c < LD_NB; c++) {
+#pragma unroll
+                for (int q = 0; q < 4; q++) {
+                    if (c >= 8 * q) {   // column k = w + 8q is zero above row k >= 8q: earlier steps do nothing
+                        const double mc = __shfl_sync(0xffffffffu, mk[q], c);
+                        mk[q] -= lrow[c] * mc;   // lrow[c] == 0 for lanes <= c
+                    }
+                }
+            }
+#pragma unroll
+            for (int q = 0; q < 4; q++) Msm[ln][w + 8 * q] = mk[q];
+        }
+        __syncthreads();
+        if (tid < nb) { const double iv = dinvv[tid]; if (!isfinite(iv) || iv == 0.0) fail = 1; }   // zero / non-finite pivot <=> its reciprocal is not a finite non-zero number
+        __syncthreads();
         SOLVE_MARK(1);
         if (fail) break;   // block-uniform and identical in every CTA of the cluster (same data)
         // (2) rows below the diagonal block (including the rhs row): a contiguous chunk of rows per CTA, 4 lanes per row, 8 columns per lane.
@@ -497,50 +530,37 @@ __global__ void __launch_bounds__(SOLVE_T) k_ba_solve(BADev D, double* __restric
         const int trR = rows - nb;
         const int chunk = (trR + C - 1) / C, r0c = crank * chunk, r1c = min(r0c + chunk, trR);
         {
+            // X = A_rows M^T (x_c = sum_{c2 <= c} a_c2 M[c][c2]), L = X / d. 4 lanes per row; lane j forms the columns j, j+4, ... (balanced: the
+            // sum for column j + 4 m runs to c2 = 4 m + 3, the entries of M above the diagonal are zeros) from the whole row held in registers.
             const int j = tid & 3, slot = tid >> 2;
-            for (int base = r0c; base < r1c; base += SOLVE_T / 4) {   // block-uniform trip count
+            for (int base = r0c; base < r1c; base += SOLVE_T / 4) {
                 const int rr = base + slot;
                 const bool valid = rr < r1c;
-                double* Arow = A + (size_t)(jb + nb + (valid ? rr : r0c)) * n + jb + 8 * j;
-                double x[8];
+                double* Arow = A + (size_t)(jb + nb + (valid ? rr : r0c)) * n + jb;
+                double av[LD_NB];
 #pragma unroll
-                for (int k = 0; k < 8; k++) x[k] = (valid && 8 * j + k < nb) ? __ldcg(Arow + k) : 0.0;
+                for (int c = 0; c < LD_NB; c++) av[c] = (valid && c < nb) ? __ldcg(Arow + c) : 0.0;
+                const double* Mj = &Msm[j][0];
 #pragma unroll
-                for (int b = 0; b < 4; b++) {
-                    if (8 * b < nb) {   // block-uniform
-                        if (j == b) {
+                for (int mq = 0; mq < LD_NB / 4; mq++) {
+                    if (4 * mq < nb) {   // block-uniform
+                        double x0 = 0, x1 = 0;
 #pragma unroll
-                            for (int k2 = 0; k2 < 8; k2++)
-#pragma unroll
-                                for (int k = k2 + 1; k < 8; k++) x[k] -= x[k2] * Pd[8 * b + k][8 * b + k2];
-                        }
-                        double v[8];
-#pragma unroll
-                        for (int k2 = 0; k2 < 8; k2++) v[k2] = __shfl_sync(0xffffffffu, x[k2], (lane & ~3) | b);
-                        if (j > b) {
-#pragma unroll
-                            for (int k2 = 0; k2 < 8; k2++)
-#pragma unroll
-                                for (int k = 0; k < 8; k++) x[k] -= v[k2] * Pd[8 * j + k][8 * b + k2];
-                        }
-                    }
-                }
-                if (valid) {
-#pragma unroll
-                    for (int k = 0; k < 8; k++) {
-                        const int c = 8 * j + k;
-                        if (c < nb) {
-                            const double lv = x[k] * dinvv[c];
-                            __stcg(Arow + k, lv);
-                            __stcg(Lt + (size_t)c * ldp + rr, lv); __stcg(LDt + (size_t)c * ldp + rr, x[k]);
+                        for (int c2 = 0; c2 < 4 * mq + 4; c2 += 2) { x0 += av[c2] * Mj[4 * mq * (LD_NB + 1) + c2]; x1 += av[c2 + 1] * Mj[4 * mq * (LD_NB + 1) + c2 + 1]; }
+                        const double x = x0 + x1;
+                        const int c = j + 4 * mq;
+                        if (valid && c < nb) {
+                            const double lv = x * dinvv[c];
+                            __stcg(Arow + c, lv);
+                            __stcg(Lt + (size_t)c * ldp + rr, lv); __stcg(LDt + (size_t)c * ldp + rr, x);
                         }
                     }
                 }
             }
         }
-        // L of the diagonal block back into S (needed by the back substitution), by cluster rank 0
+        // M of this panel to the scratch the back substitution reads (cluster rank 0)
         if (crank == 0)
-            for (int i = tid; i < nb * nb; i += SOLVE_T) { const int rr = i / nb, c = i - rr * nb; if (rr > c) __stcg(A + (size_t)(jb + rr) * n + jb + c, Pd[rr][c]); }
+            for (int i = tid; i < LD_NB * LD_NB; i += SOLVE_T) { const int rr = i / LD_NB, c = i - rr * LD_NB; __stcg(Mg + (size_t)(jb / LD_NB) * LD_NB * LD_NB + i, (rr < nb && c < nb) ? Msm[rr][c] : 0.0); }
         SOLVE_MARK(2);
         cluster.sync();
         SOLVE_MARK(3);
@@ -548,22 +568,32 @@ __global__ void __launch_bounds__(SOLVE_T) k_ba_solve(BADev D, double* __restric
         const int trC = n - jb - nb;
         if (trC > 0) {
             if (stage) {
-                const int w2 = (trR + 1) >> 1, tot = nb * w2;   // double2 words per panel row / in a panel
-                for (int i0 = tid; i0 < tot; i0 += 4 * SOLVE_T) {
-                    double2 vl[4], vd[4]; int off[4];
+                // thread (half, q): panel columns c = 2 u + half, double2 words q and q + 128 of a panel row; 8 columns (16 .. 32 loads) in flight
+                const int w2 = (trR + 1) >> 1, st2 = ldp >> 1, half = tid >> 7, q0 = tid & 127;
+                const double2* gL = reinterpret_cast<const double2*>(Lt); const double2* gD = reinterpret_cast<const double2*>(LDt);
+                double2* hL = reinterpret_cast<double2*>(sL); double2* hD = reinterpret_cast<double2*>(sLD);
+                const bool q0ok = q0 < w2, q1ok = q0 + 128 < w2;
+                for (int c0 = half; c0 < nb; c0 += 16) {
+                    double2 vl[8][2], vd[8][2];
 #pragma unroll
-                    for (int u = 0; u < 4; u++) {
-                        const int i = i0 + u * SOLVE_T;
-                        if (i < tot) {
-                            const int c = i / w2, q = i - c * w2;
-                            off[u] = c * (ldp >> 1) + q;
-                            vl[u] = __ldcg(reinterpret_cast<const double2*>(Lt) + off[u]);
-                            vd[u] = __ldcg(reinterpret_cast<const double2*>(LDt) + off[u]);
-                        } else off[u] = -1;
+                    for (int u = 0; u < 8; u++) {
+                        const int c = c0 + 2 * u;
+                        if (c < nb) {
+                            if (q0ok) { vl[u][0] = __ldcg(gL + c * st2 + q0); vd[u][0] = __ldcg(gD + c * st2 + q0); }
+                            if (q1ok) { vl[u][1] = __ldcg(gL + c * st2 + q0 + 128); vd[u][1] = __ldcg(gD + c * st2 + q0 + 128); }
+                        }
                     }
 #pragma unroll
-                    for (int u = 0; u < 4; u++) if (off[u] >= 0) { reinterpret_cast<double2*>(sL)[off[u]] = vl[u]; reinterpret_cast<double2*>(sLD)[off[u]] = vd[u]; }
+                    for (int u = 0; u < 8; u++) {
+                        const int c = c0 + 2 * u;
+                        if (c < nb) {
+                            if (q0ok) { hL[c * st2 + q0] = vl[u][0]; hD[c * st2 + q0] = vd[u][0]; }
+                            if (q1ok) { hL[c * st2 + q0 + 128] = vl[u][1]; hD[c * st2 + q0 + 128] = vd[u][1]; }
+                        }
+                    }
                 }
+                for (int q = q0 + 256; q < w2; q += 128)   // panels longer than 512 rows (not the staged regime in practice)
+                    for (int c = half; c < nb; c += 2) { hL[c * st2 + q] = __ldcg(gL + c * st2 + q); hD[c * st2 + q] = __ldcg(gD + c * st2 + q); }
                 __syncthreads();
             }
             SOLVE_MARK(4);
@@ -621,33 +651,29 @@ __global__ void __launch_bounds__(SOLVE_T) k_ba_solve(BADev D, double* __restric
     }
     if (fail) { if (crank == 0 && tid == 0) D.scal[3] = 1.0; return; }
     if (crank != 0) return;
-    // backward: L^T x = z, z = row n of L (= D^-1 L^-1 g); blocks of NB columns from the bottom
+    // backward: L^T x = z, z = row n of L (= D^-1 L^-1 g), panel by panel from the bottom: x_b = M_b^T y_b, then y_above -= L[b][above]^T x_b
     double* y = dsm + (stage ? 2 * (size_t)LD_NB * ldp : 0);
     for (int i = tid; i < n; i += SOLVE_T) y[i] = __ldcg(A + (size_t)n * n + i);
     __syncthreads();
-    for (int je = n; je > 0; je -= LD_NB) {
-        const int j0 = max(je - LD_NB, 0), nb = je - j0;
-        // rows above the block: L[j0 + j][i] for this thread's rows i (independent of the block solve -> the loads fly under it)
+    for (int pb = (n - 1) / LD_NB; pb >= 0; pb--) {
+        const int j0 = pb * LD_NB, nb = min(LD_NB, n - j0);
+        // rows above the block: L[j0 + j][i] for this thread's rows i; M_b[j][lane] for warp 0 (all independent of y: in flight together)
         double v0[LD_NB], v1[LD_NB];
-        const int i0 = tid, i1 = tid + SOLVE_T;   // n <= 2 * SOLVE_T is the staged regime; larger systems loop below
+        const int i0 = tid, i1 = tid + SOLVE_T;
 #pragma unroll
         for (int j = 0; j < LD_NB; j++) {
             v0[j] = (j < nb && i0 < j0) ? __ldcg(A + (size_t)(j0 + j) * n + i0) : 0.0;
             v1[j] = (j < nb && i1 < j0) ? __ldcg(A + (size_t)(j0 + j) * n + i1) : 0.0;
         }
-        if (tid < 32) {   // lane i owns y[j0 + i] and column i of the block: y_i -= L[j][i] x_j for j = nb-1 .. i+1
-            double yi = tid < nb ? y[j0 + tid] : 0.0;
-            double col[LD_NB];
+        if (tid < 32) {
+            double mc[LD_NB], yv[LD_NB];
 #pragma unroll
-            for (int j = 0; j < LD_NB; j++) col[j] = (j < nb && tid < j) ? __ldcg(A + (size_t)(j0 + j) * n + j0 + tid) : 0.0;
+            for (int j = 0; j < LD_NB; j++) { mc[j] = __ldcg(Mg + (size_t)pb * LD_NB * LD_NB + j * LD_NB + tid); yv[j] = j < nb ? y[j0 + j] : 0.0; }
+            double s0 = 0, s1 = 0, s2 = 0, s3 = 0;
 #pragma unroll
-            for (int j = LD_NB - 1; j >= 0; j--) {
-                if (j < nb) {
-                    const double xj = __shfl_sync(0xffffffffu, yi, j);
-                    yi -= col[j] * xj;   // col[j] == 0 for lanes >= j
-                }
-            }
-            if (tid < nb) y[j0 + tid] = yi;
+            for (int j = 0; j < LD_NB; j += 4) { s0 += mc[j] * yv[j]; s1 += mc[j + 1] * yv[j + 1]; s2 += mc[j + 2] * yv[j + 2]; s3 += mc[j + 3] * yv[j + 3]; }
+            __syncwarp();
+            if (tid < nb) y[j0 + tid] = (s0 + s1) + (s2 + s3);
         }
         __syncthreads();
         {
@@ -693,7 +719,7 @@ __global__ void __launch_bounds__(128) k_ba_backsub(BADev D) {
     if (!act) { D.xl[3 * l] = 0; D.xl[3 * l + 1] = 0; D.xl[3 * l + 2] = 0; return; }
 #pragma unroll
     for (int j = 0; j < 3; j++) cl[j] = D.bl[3 * l + j] - cl[j];
-    const double* Di = D.Dinv + 9 * (size_t)l;
+    const double* Di = D.Dinv + DINV_LD * (size_t)l;
 #pragma unroll
     for (int i = 0; i < 3; i++) D.xl[3 * l + i] = Di[3 * i] * cl[0] + Di[3 * i + 1] * cl[1] + Di[3 * i + 2] * cl[2];
 }
@@ -930,7 +956,7 @@ struct BAHost {
     std::vector<int> perm;            // sorted edge position -> caller's edge index
     std::vector<uint8_t> level; std::vector<int> poseIdx; std::vector<uint8_t> ptAct, fixed;
     int* d_poseIdx = nullptr; uint8_t* d_ptAct = nullptr; uint8_t* d_flag = nullptr;
-    double* Lt = nullptr; double* LDt = nullptr; int ldp = 0;
+    double* Lt = nullptr; double* LDt = nullptr; double* Minv = nullptr; int ldp = 0;   // panel buffers, inverses of the diagonal blocks' unit factors
     double* red = nullptr;            // private reduce buffer [S | g | bpr | tail]
     double* HppFull = nullptr;        // multi-GPU: all-reduced copy of the pose blocks for computeLambdaInit
     size_t xstride = 0;               // one-shot path: doubles between the two payload buffers of an exchange region
@@ -1060,7 +1086,7 @@ struct BAHost {
             cudaLaunchAttribute at[1];
             at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = o->clusterSize; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
             cfg.attrs = at; cfg.numAttrs = 1;
-            CSLAM_CUDA(cudaLaunchKernelEx(&cfg, k_ba_solve, R, Lt, LDt, ldp, stage, d_prof)); o->launches++;
+            CSLAM_CUDA(cudaLaunchKernelEx(&cfg, k_ba_solve, R, Lt, LDt, Minv, ldp, stage, d_prof)); o->launches++;
         }
         tick(BK_BACKSUB);
         k_ba_backsub<<<grid(D.nMP * LM_LANES, 128), 128, 0, o->stream>>>(D); o->launches++;
@@ -1191,6 +1217,10 @@ extern "C" int cslam_local_ba(cslam_optimizer* o, cslam_ba_problem* p, const vol
     if (p->face_w != p->face_h || p->face_w <= 0) { set_error("cube faces must be square"); return CSLAM_E_BADARG; }
     CSLAM_CUDA(cudaSetDevice(o->device));
     free_pool(o);
+    const bool hostProf = getenv("CSLAM_BA_PROFILE") != nullptr;
+    auto tNow = []() { return std::chrono::steady_clock::now(); };
+    auto tMs = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) { return std::chrono::duration<double, std::milli>(b - a).count(); };
+    const auto tp0 = tNow();
     const int nKF = p->n_kf, nMP = p->n_mp, nE = p->n_edges;
     if (r) { r->iterations = 0; r->trials = 0; if (r->outlier) std::memset(r->outlier, 0, nE); }
     if (stop_flag && *stop_flag) return CSLAM_OK;   // src/Optimizer.cpp:359-361
@@ -1242,6 +1272,7 @@ extern "C" int cslam_local_ba(cslam_optimizer* o, cslam_ba_problem* p, const vol
     D.nQ = nQ;
     int rc;
     const int nmax = 6 * nQ;
+    const auto tp1 = tNow();
     const Pose* cpose = nullptr; const double* cX = nullptr;
     if ((rc = dupload(o, &cpose, poses)) || (rc = dupload(o, &cX, X)) || (rc = dupload(o, &D.eMP, H.h_eMP)) || (rc = dupload(o, &D.eKF, H.h_eKF)) ||
         (rc = dupload(o, &D.obs, obs)) || (rc = dupload(o, &D.face, face)) || (rc = dupload(o, &D.lmStart, lmStart)) || (rc = dupload(o, &D.peStart, peStart)) ||
@@ -1254,10 +1285,10 @@ extern "C" int cslam_local_ba(cslam_optimizer* o, cslam_ba_problem* p, const vol
     if ((rc = dalloc(o, &D.poseBak, nKF)) || (rc = dalloc(o, &D.Xbak, (size_t)nMP * 3)) || (rc = dalloc(o, &D.err, (size_t)nE * 2, true)) || (rc = dalloc(o, &D.level, nE, true)) ||
         (rc = dalloc(o, &H.d_poseIdx, nKF)) || (rc = dalloc(o, &H.d_ptAct, nMP)) || (rc = dalloc(o, &H.d_flag, nE)) || (rc = dalloc(o, &D.Hpp, (size_t)std::max(nQ, 1) * 36)) ||
         (rc = dalloc(o, &D.bp, (size_t)std::max(nQ, 1) * 6)) || (rc = dalloc(o, &D.Hll, (size_t)nMP * 9)) || (rc = dalloc(o, &D.bl, (size_t)nMP * 3)) ||
-        (rc = dalloc(o, &D.Hpl, (size_t)nE * 18)) || (rc = dalloc(o, &D.Dinv, (size_t)nMP * 9)) || (rc = dalloc(o, &D.db, (size_t)nMP * 3)) ||
+        (rc = dalloc(o, &D.Hpl, (size_t)nE * 18)) || (rc = dalloc(o, &D.Dinv, (size_t)nMP * DINV_LD)) || (rc = dalloc(o, &D.db, (size_t)nMP * 3)) ||
         (rc = dalloc(o, &H.red, payloadMax)) || (rc = dalloc(o, &D.xp, std::max(nmax, 1), true)) || (rc = dalloc(o, &D.xl, (size_t)nMP * 3, true)) ||
         (rc = dalloc(o, &D.scal, 8, true)) || (rc = dalloc(o, &D.part, maxBlocks)) || (rc = dalloc(o, &D.ticket, 4, true)) || (rc = dalloc(o, &D.posePart, (size_t)std::max(nQ, 1) * POSE_SPLIT * 27)) || (rc = dalloc(o, &D.poseTicket, std::max(nQ, 1), true)) ||
-        (rc = dalloc(o, &H.Lt, (size_t)LD_NB * H.ldp)) || (rc = dalloc(o, &H.LDt, (size_t)LD_NB * H.ldp)) || (rc = dalloc(o, &pairCnt, (size_t)nQ * nQ + 1)) ||
+        (rc = dalloc(o, &H.Lt, (size_t)LD_NB * H.ldp)) || (rc = dalloc(o, &H.LDt, (size_t)LD_NB * H.ldp)) || (rc = dalloc(o, &H.Minv, (size_t)(nmax / LD_NB + 1) * LD_NB * LD_NB)) || (rc = dalloc(o, &pairCnt, (size_t)nQ * nQ + 1)) ||
         (rc = dalloc(o, &H.d_xerr, 1, true))) return rc;
     D.poseIdx = H.d_poseIdx; D.ptAct = H.d_ptAct;
     if (getenv("CSLAM_BA_PROFILE")) { if ((rc = dalloc(o, &H.d_prof, 8, true))) return rc; }
@@ -1284,6 +1315,8 @@ extern "C" int cslam_local_ba(cslam_optimizer* o, cslam_ba_problem* p, const vol
         CSLAM_CUDA(cudaGetLastError());
         D.pairStart = pairCnt; D.tuples = tuples;
     }
+    if (hostProf) cudaStreamSynchronize(o->stream);
+    const auto tp2 = tNow();
     // ---- src/Optimizer.cpp:363-395
     if ((rc = H.initialize())) return rc;
     if ((rc = H.optimize(its1))) return rc;
@@ -1296,6 +1329,7 @@ extern "C" int cslam_local_ba(cslam_optimizer* o, cslam_ba_problem* p, const vol
         if ((rc = H.optimize(its2))) return rc;
     }
     if ((rc = H.classify(flags))) return rc;
+    const auto tp3 = tNow();
     H.drop_graph();
     if (H.d_prof) {
         long long hp[8]; cudaMemcpyAsync(hp, H.d_prof, sizeof(hp), cudaMemcpyDeviceToHost, o->stream); cudaStreamSynchronize(o->stream);
@@ -1320,5 +1354,6 @@ extern "C" int cslam_local_ba(cslam_optimizer* o, cslam_ba_problem* p, const vol
         r->iterations = H.iterations; r->trials = H.trials;
     }
     free_pool(o);
+    if (hostProf) std::fprintf(stderr, "[cslam_local_ba] host prep %.3f ms, upload + co-observation lists %.3f ms, LM schedule %.3f ms (%d trials), write-back %.3f ms\n", tMs(tp0, tp1), tMs(tp1, tp2), tMs(tp2, tp3), H.trials, tMs(tp3, tNow()));
     return CSLAM_OK;
 }
