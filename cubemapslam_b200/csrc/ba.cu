@@ -950,10 +950,37 @@ extern "C" int cslam_optimizer_init_nccl(cslam_optimizer* o, const uint8_t id128
     return CSLAM_OK;
 }
 
+// Per-edge input conversion on the device (was a host loop): cube face of the key point (CamModelGeneral::FaceInCubemap(cv::Point2f),
+// float arithmetic as the reference), position inside the face as double (GetPosInFace<double>), information weight; s = position in the
+// landmark-sorted order, perm[s] = the caller's edge index (perm == nullptr: the caller's order is already grouped by landmark).
+__global__ void __launch_bounds__(256) k_ba_prep_edges(int nE, const int* __restrict__ perm, const float2* __restrict__ kp, const float* __restrict__ isig, int faceW, int faceH,
+                                                       double* __restrict__ obs, int8_t* __restrict__ face, int* __restrict__ bad) {
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= nE) return;
+    const int e = perm ? perm[s] : s;
+    const float2 k = kp[e];
+    const float fi = __fdiv_rn(k.x, (float)faceW), fj = __fdiv_rn(k.y, (float)faceH);
+    int f = -1;
+    if (fi >= 0 && fi < 1 && fj >= 1 && fj < 2) f = 1;
+    else if (fi >= 1 && fi < 2 && fj >= 0 && fj < 1) f = 3;
+    else if (fi >= 1 && fi < 2 && fj >= 1 && fj < 2) f = 0;
+    else if (fi >= 1 && fi < 2 && fj >= 2 && fj < 3) f = 4;
+    else if (fi >= 2 && fi < 3 && fj >= 1 && fj < 2) f = 2;
+    if (f < 0) atomicMin(bad, e);
+    face[s] = (int8_t)f;
+    obs[3 * s] = (double)k.x - floor((double)k.x / faceW) * faceW;
+    obs[3 * s + 1] = (double)k.y - floor((double)k.y / faceH) * faceH;
+    obs[3 * s + 2] = (double)isig[e];
+}
+__global__ void __launch_bounds__(256) k_ba_prep_points(int n3, const float* __restrict__ in, double* __restrict__ out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n3) out[i] = (double)in[i];
+}
+
 namespace {
 struct BAHost {
     cslam_optimizer* o; BADev D; cslam_ba_result* res;
-    std::vector<int> perm;            // sorted edge position -> caller's edge index
+    const int* perm = nullptr;        // sorted edge position -> caller's edge index; nullptr = identity (input already grouped by landmark)
     std::vector<uint8_t> level; std::vector<int> poseIdx; std::vector<uint8_t> ptAct, fixed;
     int* d_poseIdx = nullptr; uint8_t* d_ptAct = nullptr; uint8_t* d_flag = nullptr;
     double* Lt = nullptr; double* LDt = nullptr; double* Minv = nullptr; int ldp = 0;   // panel buffers, inverses of the diagonal blocks' unit factors
@@ -964,7 +991,7 @@ struct BAHost {
     long long* d_prof = nullptr;      // CSLAM_BA_PROFILE=1: clock64 per solver phase (debug)
     double lambda = -1, ni = 2; int nBad = 0; int iterations = 0, trials = 0;
     const volatile uint8_t* stop = nullptr;
-    std::vector<int> h_eMP, h_eKF; int nActive = 0;
+    const int* h_eMP = nullptr; const int* h_eKF = nullptr; int nActive = 0;   // landmark-sorted edge endpoints on the host
     bool useOneShot = false;
     bool terminate() const { return stop ? (*stop != 0) : false; }
     int grid(int n, int t = 256) const { return std::max(1, cdiv(n, t)); }
@@ -991,7 +1018,7 @@ struct BAHost {
     int initialize() {
         std::vector<uint8_t> pAct(D.nKF, 0);
         std::fill(ptAct.begin(), ptAct.end(), 0);
-        const int* eMP = h_eMP.data(); const int* eKF = h_eKF.data();
+        const int* eMP = h_eMP; const int* eKF = h_eKF;
         for (int e = 0; e < D.nE; e++) if (level[e] == 0) { pAct[eKF[e]] = 1; ptAct[eMP[e]] = 1; }
         int nP = 0;
         for (int k = 0; k < D.nKF; k++) poseIdx[k] = (pAct[k] && !fixed[k]) ? nP++ : -1;
@@ -1228,43 +1255,32 @@ extern "C" int cslam_local_ba(cslam_optimizer* o, cslam_ba_problem* p, const vol
     BADev& D = H.D; std::memset(&D, 0, sizeof(D));
     D.nKF = nKF; D.nMP = nMP; D.nE = nE; D.f = p->face_w / 2.0; D.rank = o->rank; D.nranks = o->nranks;
     const float dlt = (float)std::sqrt(5.991); D.delta = (double)dlt; D.dsqr = D.delta * D.delta; D.robust = 1;
-    // ---- edges sorted by landmark (stable), CSR by landmark and by keyframe
-    H.perm.resize(nE);
-    std::vector<int> cnt(nMP + 1, 0);
+    // ---- edges sorted by landmark (stable), CSR by landmark and by keyframe. Host work is two passes over the endpoint arrays (in scratch
+    // vectors that live in the optimizer object: no page faults per call); the per-edge float work happens on the device (k_ba_prep_edges).
+    cslam_optimizer::HostScratch& hs = o->hs;
+    hs.lmStart.assign(nMP + 1, 0);
+    bool grouped = true;
     for (int e = 0; e < nE; e++) {
-        if (p->edge_mp[e] < 0 || p->edge_mp[e] >= nMP || p->edge_kf[e] < 0 || p->edge_kf[e] >= nKF) { set_error("edge %d references a vertex out of range", e); return CSLAM_E_BADARG; }
-        cnt[p->edge_mp[e] + 1]++;
+        const int l = p->edge_mp[e], k = p->edge_kf[e];
+        if (l < 0 || l >= nMP || k < 0 || k >= nKF) { set_error("edge %d references a vertex out of range", e); return CSLAM_E_BADARG; }
+        hs.lmStart[l + 1]++;
+        if (e && l < p->edge_mp[e - 1]) grouped = false;
     }
-    for (int l = 0; l < nMP; l++) cnt[l + 1] += cnt[l];
-    std::vector<int> lmStart(cnt), fill(cnt.begin(), cnt.end() - 1);
-    for (int e = 0; e < nE; e++) H.perm[fill[p->edge_mp[e]]++] = e;
-    H.h_eMP.resize(nE); H.h_eKF.resize(nE);
-    std::vector<double> obs((size_t)nE * 3); std::vector<int8_t> face(nE);
-    for (int s = 0; s < nE; s++) {
-        const int e = H.perm[s];
-        H.h_eMP[s] = p->edge_mp[e]; H.h_eKF[s] = p->edge_kf[e];
-        const float kx = p->kp_xy[2 * e], ky = p->kp_xy[2 * e + 1];
-        const float fi = kx / (float)p->face_w, fj = ky / (float)p->face_h;   // FaceInCubemap(cv::Point2f)
-        int f = -1;
-        if (fi >= 0 && fi < 1 && fj >= 1 && fj < 2) f = 1;
-        else if (fi >= 1 && fi < 2 && fj >= 0 && fj < 1) f = 3;
-        else if (fi >= 1 && fi < 2 && fj >= 1 && fj < 2) f = 0;
-        else if (fi >= 1 && fi < 2 && fj >= 2 && fj < 3) f = 4;
-        else if (fi >= 2 && fi < 3 && fj >= 1 && fj < 2) f = 2;
-        if (f < 0) { set_error("edge %d: keypoint (%g,%g) is on no cube face (the reference calls exit() here)", e, kx, ky); return CSLAM_E_BADARG; }
-        face[s] = (int8_t)f;
-        obs[3 * s] = (double)kx - std::floor((double)kx / p->face_w) * p->face_w;     // GetPosInFace<double>
-        obs[3 * s + 1] = (double)ky - std::floor((double)ky / p->face_h) * p->face_h;
-        obs[3 * s + 2] = (double)p->inv_sigma2[e];
+    for (int l = 0; l < nMP; l++) hs.lmStart[l + 1] += hs.lmStart[l];
+    if (grouped) { H.perm = nullptr; H.h_eMP = p->edge_mp; H.h_eKF = p->edge_kf; }
+    else {
+        hs.perm.resize(nE); hs.eMP.resize(nE); hs.eKF.resize(nE); hs.fill.assign(hs.lmStart.begin(), hs.lmStart.end() - 1);
+        for (int e = 0; e < nE; e++) hs.perm[hs.fill[p->edge_mp[e]]++] = e;
+        for (int s = 0; s < nE; s++) { const int e = hs.perm[s]; hs.eMP[s] = p->edge_mp[e]; hs.eKF[s] = p->edge_kf[e]; }
+        H.perm = hs.perm.data(); H.h_eMP = hs.eMP.data(); H.h_eKF = hs.eKF.data();
     }
-    std::vector<int> peStart(nKF + 1, 0), peList(nE);
-    for (int s = 0; s < nE; s++) peStart[H.h_eKF[s] + 1]++;
-    for (int k = 0; k < nKF; k++) peStart[k + 1] += peStart[k];
-    { std::vector<int> f2(peStart.begin(), peStart.end() - 1); for (int s = 0; s < nE; s++) peList[f2[H.h_eKF[s]]++] = s; }
+    hs.peStart.assign(nKF + 1, 0); hs.peList.resize(nE);
+    for (int s = 0; s < nE; s++) hs.peStart[H.h_eKF[s] + 1]++;
+    for (int k = 0; k < nKF; k++) hs.peStart[k + 1] += hs.peStart[k];
+    hs.fill.assign(hs.peStart.begin(), hs.peStart.end() - 1);
+    for (int s = 0; s < nE; s++) hs.peList[hs.fill[H.h_eKF[s]]++] = s;
     std::vector<Pose> poses(nKF);
     for (int k = 0; k < nKF; k++) poses[k] = pose_from_Tcw32(p->Tcw + 16 * k);
-    std::vector<double> X((size_t)nMP * 3);
-    for (size_t i = 0; i < X.size(); i++) X[i] = (double)p->points[i];
     H.fixed.assign(p->kf_fixed, p->kf_fixed + nKF); H.level.assign(nE, 0); H.poseIdx.assign(nKF, -1); H.ptAct.assign(nMP, 0);
     std::vector<int> kfOfQ;
     for (int k = 0; k < nKF; k++) if (!H.fixed[k]) kfOfQ.push_back(k);
@@ -1273,11 +1289,26 @@ extern "C" int cslam_local_ba(cslam_optimizer* o, cslam_ba_problem* p, const vol
     int rc;
     const int nmax = 6 * nQ;
     const auto tp1 = tNow();
-    const Pose* cpose = nullptr; const double* cX = nullptr;
-    if ((rc = dupload(o, &cpose, poses)) || (rc = dupload(o, &cX, X)) || (rc = dupload(o, &D.eMP, H.h_eMP)) || (rc = dupload(o, &D.eKF, H.h_eKF)) ||
-        (rc = dupload(o, &D.obs, obs)) || (rc = dupload(o, &D.face, face)) || (rc = dupload(o, &D.lmStart, lmStart)) || (rc = dupload(o, &D.peStart, peStart)) ||
-        (rc = dupload(o, &D.peList, peList)) || (rc = dupload(o, &D.kfOfQ, kfOfQ))) return rc;
-    D.pose = const_cast<Pose*>(cpose); D.X = const_cast<double*>(cX);
+    const Pose* cpose = nullptr; double* cX = nullptr;
+    int* d_eMP = nullptr; int* d_eKF = nullptr; int* d_perm = nullptr; float2* d_kp = nullptr; float* d_isig = nullptr; float* d_pts32 = nullptr; int* d_bad = nullptr;
+    double* d_obs = nullptr; int8_t* d_face = nullptr;
+    if ((rc = dupload(o, &cpose, poses)) || (rc = dupload(o, &D.lmStart, hs.lmStart)) || (rc = dupload(o, &D.peStart, hs.peStart)) || (rc = dupload(o, &D.peList, hs.peList)) ||
+        (rc = dupload(o, &D.kfOfQ, kfOfQ)) || (rc = dalloc(o, &d_eMP, nE)) || (rc = dalloc(o, &d_eKF, nE)) || (rc = dalloc(o, &d_kp, nE)) || (rc = dalloc(o, &d_isig, nE)) ||
+        (rc = dalloc(o, &d_pts32, (size_t)nMP * 3)) || (rc = dalloc(o, &cX, (size_t)nMP * 3)) || (rc = dalloc(o, &d_obs, (size_t)nE * 3)) || (rc = dalloc(o, &d_face, nE)) ||
+        (rc = dalloc(o, &d_bad, 1)) || (!grouped && (rc = dalloc(o, &d_perm, nE)))) return rc;
+    if (nE > 0) {
+        CSLAM_CUDA(cudaMemcpyAsync(d_eMP, H.h_eMP, (size_t)nE * 4, cudaMemcpyHostToDevice, o->stream));
+        CSLAM_CUDA(cudaMemcpyAsync(d_eKF, H.h_eKF, (size_t)nE * 4, cudaMemcpyHostToDevice, o->stream));
+        CSLAM_CUDA(cudaMemcpyAsync(d_kp, p->kp_xy, (size_t)nE * 8, cudaMemcpyHostToDevice, o->stream));
+        CSLAM_CUDA(cudaMemcpyAsync(d_isig, p->inv_sigma2, (size_t)nE * 4, cudaMemcpyHostToDevice, o->stream));
+        if (!grouped) CSLAM_CUDA(cudaMemcpyAsync(d_perm, H.perm, (size_t)nE * 4, cudaMemcpyHostToDevice, o->stream));
+    }
+    if (nMP > 0) CSLAM_CUDA(cudaMemcpyAsync(d_pts32, p->points, (size_t)nMP * 12, cudaMemcpyHostToDevice, o->stream));
+    CSLAM_CUDA(cudaMemsetAsync(d_bad, 0x7f, sizeof(int), o->stream));
+    if (nE > 0) { k_ba_prep_edges<<<cdiv(nE, 256), 256, 0, o->stream>>>(nE, d_perm, d_kp, d_isig, p->face_w, p->face_h, d_obs, d_face, d_bad); o->launches++; }
+    if (nMP > 0) { k_ba_prep_points<<<cdiv(nMP * 3, 256), 256, 0, o->stream>>>(nMP * 3, d_pts32, cX); o->launches++; }
+    D.eMP = d_eMP; D.eKF = d_eKF; D.obs = d_obs; D.face = d_face;
+    D.pose = const_cast<Pose*>(cpose); D.X = cX;
     H.ldp = ((nmax + 1 + 8) + 3) & ~3;
     const size_t payloadMax = (size_t)nmax * nmax + 2 * (size_t)nmax + 4;
     const int maxBlocks = std::max({cdiv(nE, 256), cdiv(nmax + 3 * nMP, 256), 1});
@@ -1303,17 +1334,25 @@ extern "C" int cslam_local_ba(cslam_optimizer* o, cslam_ba_problem* p, const vol
         if ((rc = dalloc(o, &H.HppFull, (size_t)std::max(nQ, 1) * 36))) return rc;
     }
     // ---- co-observation lists (once per call, all edges)
+    int badEdge = 0x7f7f7f7f;
     if (nQ > 0) {
         k_ba_pairs_count<<<dim3(nQ, nQ), 128, 0, o->stream>>>(D, pairCnt); o->launches++;
         k_ba_pairs_scan<<<1, 1024, 0, o->stream>>>(pairCnt, nQ * nQ); o->launches++;
         long long total = 0;
         CSLAM_CUDA(cudaMemcpyAsync(&total, pairCnt + (size_t)nQ * nQ, sizeof(long long), cudaMemcpyDeviceToHost, o->stream));
+        CSLAM_CUDA(cudaMemcpyAsync(&badEdge, d_bad, sizeof(int), cudaMemcpyDeviceToHost, o->stream));
         CSLAM_CUDA(cudaStreamSynchronize(o->stream));
+        if (badEdge < nE) { set_error("edge %d: keypoint (%g,%g) is on no cube face (the reference calls exit() here)", badEdge, p->kp_xy[2 * badEdge], p->kp_xy[2 * badEdge + 1]); return CSLAM_E_BADARG; }
         int2* tuples = nullptr;
         if ((rc = dalloc(o, &tuples, (size_t)std::max<long long>(total, 1)))) return rc;
         k_ba_pairs_fill<<<dim3(nQ, nQ), 128, 0, o->stream>>>(D, pairCnt, tuples); o->launches++;
         CSLAM_CUDA(cudaGetLastError());
         D.pairStart = pairCnt; D.tuples = tuples;
+    }
+    if (nQ == 0) {
+        CSLAM_CUDA(cudaMemcpyAsync(&badEdge, d_bad, sizeof(int), cudaMemcpyDeviceToHost, o->stream));
+        CSLAM_CUDA(cudaStreamSynchronize(o->stream));
+        if (badEdge < nE) { set_error("edge %d: keypoint (%g,%g) is on no cube face (the reference calls exit() here)", badEdge, p->kp_xy[2 * badEdge], p->kp_xy[2 * badEdge + 1]); return CSLAM_E_BADARG; }
     }
     if (hostProf) cudaStreamSynchronize(o->stream);
     const auto tp2 = tNow();
@@ -1342,6 +1381,8 @@ extern "C" int cslam_local_ba(cslam_optimizer* o, cslam_ba_problem* p, const vol
         if ((rc = H.allreduce(D.X, (size_t)nMP * 3, NCCL_SUM))) return rc;
     }
     CSLAM_CUDA(cudaMemcpyAsync(poses.data(), D.pose, nKF * sizeof(Pose), cudaMemcpyDeviceToHost, o->stream));
+    hs.X.resize((size_t)nMP * 3);
+    std::vector<double>& X = hs.X;
     CSLAM_CUDA(cudaMemcpyAsync(X.data(), D.X, X.size() * 8, cudaMemcpyDeviceToHost, o->stream));
     CSLAM_CUDA(cudaStreamSynchronize(o->stream));
     for (int k = 0; k < nKF; k++) {
@@ -1350,7 +1391,7 @@ extern "C" int cslam_local_ba(cslam_optimizer* o, cslam_ba_problem* p, const vol
     }
     for (size_t i = 0; i < X.size(); i++) { p->points[i] = (float)X[i]; if (r && r->points_fp64) r->points_fp64[i] = X[i]; }
     if (r) {
-        if (r->outlier) for (int s = 0; s < nE; s++) r->outlier[H.perm[s]] = flags[s];
+        if (r->outlier) for (int s = 0; s < nE; s++) r->outlier[H.perm ? H.perm[s] : s] = flags[s];
         r->iterations = H.iterations; r->trials = H.trials;
     }
     free_pool(o);

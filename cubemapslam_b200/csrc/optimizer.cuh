@@ -18,6 +18,8 @@ struct cslam_optimizer {
     double* h_scal = nullptr;   // pinned, 16 doubles
     int clusterSize = 8;        // CTAs of the reduced-camera-system solver cluster
     bool useGraphs = true;      // single-GPU LM trials are replayed as one CUDA graph (CSLAM_BA_GRAPH=0 disables)
+    // host scratch of cslam_local_ba, kept across calls (fresh multi-megabyte vectors cost page faults on every call)
+    struct HostScratch { std::vector<int> lmStart, perm, eMP, eKF, fill, peStart, peList; std::vector<double> X; } hs;
     // optional per-kernel timing (cslam_optimizer_set_timing)
     bool timing = false; std::vector<cudaEvent_t> ev; std::vector<int> evKind; int evUsed = 0; double kindMs[16] = {0}; int64_t kindCount[16] = {0};
     // one-shot NVLink all-reduce of the reduced camera system (multi-GPU LocalBA): peer views of every rank's exchange buffer

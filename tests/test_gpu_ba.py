@@ -106,3 +106,23 @@ def test_config4_vs_oracle(oracle, opt):
     p = synth.ba_problem()
     r, g = _compare_ba(oracle, opt, p)
     assert len(p["eMP"]) > 150000 and r["iters"] >= 5
+
+
+def test_local_ba_edge_order_is_free(oracle, opt):
+    """Edges may come in any order (the drop-in emits them per MapPoint, other callers may not): a shuffled edge list takes the host counting
+    sort + device gather path and must give the same answer as the grouped list, flags returned in the caller's order. A key point on no cube
+    face is reported as an error naming the caller's edge index (the reference calls exit() there, src/CamModelGeneral.cpp FaceInCubemap)."""
+    p = synth.ba_problem(nKF=8, nMP=300, kmin=2, kmax=6, faceW=450, seed=13, radius=1.5)
+    g0 = opt.LocalBundleAdjustment(p["Tcw"], p["kf_fixed"], p["pts"], p["eMP"], p["eKF"], p["kpxy"], p["inv_sigma2"], 450, 450)
+    perm = np.random.default_rng(5).permutation(len(p["eMP"]))
+    q = {k: (np.ascontiguousarray(p[k][perm]) if k in ("eMP", "eKF", "kpxy", "inv_sigma2") else p[k]) for k in p}
+    g1 = opt.LocalBundleAdjustment(q["Tcw"], q["kf_fixed"], q["pts"], q["eMP"], q["eKF"], q["kpxy"], q["inv_sigma2"], 450, 450)
+    r = oracle.local_ba(q["Tcw"], q["kf_fixed"], q["pts"], q["eMP"], q["eKF"], q["kpxy"], q["inv_sigma2"], 450, 450)
+    assert g1["iters"] == g0["iters"] == r["iters"]
+    assert np.array_equal(g1["outlier"], g0["outlier"][perm]) and np.array_equal(g1["outlier"], r["outlier"])
+    # a stable sort by landmark restores the grouped order edge for edge only if the shuffle kept the per-landmark order; sums are reordered otherwise
+    assert rel(g1["pose64"], g0["pose64"]) < 1e-9 and rel(g1["pts64"], g0["pts64"]) < 1e-9
+    assert rel(g1["pose64"], r["pose64"]) < RTOL
+    bad = q["kpxy"].copy(); bad[17] = (10.0, 10.0)    # top-left corner of the canvas: no face
+    with pytest.raises(Exception, match="edge 17"):
+        opt.LocalBundleAdjustment(q["Tcw"], q["kf_fixed"], q["pts"], q["eMP"], q["eKF"], bad, q["inv_sigma2"], 450, 450)
