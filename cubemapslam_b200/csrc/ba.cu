@@ -804,6 +804,38 @@ __global__ void __launch_bounds__(256) k_ba_xchg_reduce(XchgPeers P, unsigned ep
     }
 }
 
+// The scalars of a trial (chi2, scale; lambda_init's max diagonal) travel the same way: <= 4 doubles per rank in a double-buffered slot of
+// the exchange region, one warp, one launch, fixed rank order (instead of a ~30 us ncclAllReduce per trial and per iteration).
+struct SmallPeers { volatile unsigned* flags[8]; const double* slot[8]; double* mine; int n, rank; };
+__global__ void k_ba_small_xchg(SmallPeers P, unsigned epoch, const double* src, double* dst, int count, int isMax, int* err) {
+    const int t = threadIdx.x;
+    double* slot = P.mine + (epoch & 1) * 4;
+    if (t < count) slot[t] = src[t];
+    __threadfence_system();
+    __syncwarp();
+    if (t < P.n) P.flags[t][P.rank] = epoch;
+    __threadfence_system();
+    bool ok = true;
+    if (t < P.n) {
+        volatile unsigned* mine = P.flags[P.rank];
+        long long spins = 0;
+        while ((int)(mine[t] - epoch) < 0) { if (++spins > (1ll << 26)) { ok = false; break; } __nanosleep(32); }
+    }
+    ok = __all_sync(0xffffffffu, ok);
+    __threadfence_system();
+    if (!ok) { if (t == 0) *err = 1; return; }
+    if (t < count) {
+        double v = __ldcv(P.slot[0] + (epoch & 1) * 4 + t);
+        for (int r = 1; r < P.n; r++) { const double u = __ldcv(P.slot[r] + (epoch & 1) * 4 + t); v = isMax ? fmax(v, u) : v + u; }
+        dst[t] = v;
+    }
+}
+// multi-GPU: a rank classifies the edges of its own landmarks; the flags go to the caller's edge positions of a zeroed array that is max-reduced
+__global__ void __launch_bounds__(256) k_ba_scatter_flags(int nLocal, const int* __restrict__ perm, const uint8_t* __restrict__ flag, uint8_t* __restrict__ out) {
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s < nLocal) out[perm[s]] = flag[s];
+}
+
 }  // namespace cslam
 
 // =================================================================================================== host side
@@ -836,7 +868,7 @@ static NcclApi* nccl_api() {
     if (!api.GetUniqueId || !api.CommInitRank || !api.AllReduce || !api.CommDestroy) { dlclose(api.h); api.h = nullptr; return nullptr; }
     return &api;
 }
-enum { NCCL_U8 = 1, NCCL_F64 = 8, NCCL_SUM = 0, NCCL_MAX = 2 };
+enum { NCCL_U8 = 1, NCCL_I32 = 2, NCCL_F64 = 8, NCCL_SUM = 0, NCCL_MAX = 2 };
 enum { BK_ERRORS = 0, BK_LIN_POINTS, BK_LIN_POSES, BK_DINV, BK_SCHUR, BK_XCHG, BK_SOLVE, BK_BACKSUB, BK_UPDATE, BK_SCALE, BK_END, BK_COUNT };
 static const char* kBaKindNames[BK_COUNT] = {"k_ba_errors", "k_ba_lin_points", "k_ba_lin_poses", "k_ba_dinv", "k_ba_schur", "exchange", "k_ba_solve", "k_ba_backsub", "k_ba_update", "k_ba_scale", "end"};
 
@@ -934,7 +966,7 @@ static int setup_xchg(cslam_optimizer* o, size_t payloadBytes) {
     CSLAM_CUDA(cudaStreamSynchronize(o->stream));
     cudaFree(flag);
     if (rc || bad != 0.0) return 1;
-    o->xchgBytes = payloadBytes; o->oneShot = true; o->epoch = 0;
+    o->xchgBytes = payloadBytes; o->oneShot = true; o->epoch = 0; o->epoch2 = 0;
     return 0;
 }
 
@@ -982,7 +1014,7 @@ struct BAHost {
     cslam_optimizer* o; BADev D; cslam_ba_result* res;
     const int* perm = nullptr;        // sorted edge position -> caller's edge index; nullptr = identity (input already grouped by landmark)
     std::vector<uint8_t> level; std::vector<int> poseIdx; std::vector<uint8_t> ptAct, fixed;
-    int* d_poseIdx = nullptr; uint8_t* d_ptAct = nullptr; uint8_t* d_flag = nullptr;
+    int* d_poseIdx = nullptr; uint8_t* d_ptAct = nullptr; uint8_t* d_flag = nullptr; int* d_pact = nullptr;
     double* Lt = nullptr; double* LDt = nullptr; double* Minv = nullptr; int ldp = 0;   // panel buffers, inverses of the diagonal blocks' unit factors
     double* red = nullptr;            // private reduce buffer [S | g | bpr | tail]
     double* HppFull = nullptr;        // multi-GPU: all-reduced copy of the pose blocks for computeLambdaInit
@@ -990,6 +1022,7 @@ struct BAHost {
     int* d_xerr = nullptr;
     long long* d_prof = nullptr;      // CSLAM_BA_PROFILE=1: clock64 per solver phase (debug)
     double lambda = -1, ni = 2; int nBad = 0; int iterations = 0, trials = 0;
+    bool errorsCurrent = false; double lastChi = 0;   // D.err / chi2 belong to the current state (set by an accepted trial)
     const volatile uint8_t* stop = nullptr;
     const int* h_eMP = nullptr; const int* h_eKF = nullptr; int nActive = 0;   // landmark-sorted edge endpoints on the host
     bool useOneShot = false;
@@ -1001,6 +1034,17 @@ struct BAHost {
         if (o->nranks <= 1) return 0;
         int rc = nccl_api()->AllReduce(buf, buf, count, NCCL_F64, op, o->comm, o->stream);
         if (rc) { set_error("ncclAllReduce failed (%d)", rc); return CSLAM_E_NCCL; }
+        return 0;
+    }
+    // <= 4 doubles, in place: the one-shot path when the peer views exist, NCCL otherwise
+    int allreduce_small(double* buf, int count, bool isMax) {
+        if (o->nranks <= 1) return 0;
+        if (!useOneShot) return allreduce(buf, count, isMax ? NCCL_MAX : NCCL_SUM);
+        SmallPeers P; P.n = o->nranks; P.rank = o->rank;
+        const size_t off = 2 * xstride * 8;
+        for (int r = 0; r < o->nranks; r++) { P.flags[r] = (volatile unsigned*)((char*)o->peers[r].base + off + 64); P.slot[r] = (const double*)((char*)o->peers[r].base + off + 128); }
+        P.mine = (double*)((char*)o->peers[o->rank].base + off + 128);
+        k_ba_small_xchg<<<1, 32, 0, o->stream>>>(P, ++o->epoch2, buf, buf, count, isMax ? 1 : 0, d_xerr); o->launches++;
         return 0;
     }
     int fetch(const double* src, int count) {
@@ -1016,17 +1060,27 @@ struct BAHost {
 
     // initializeOptimization(level 0): active edges, active vertices, compact pose indices (sparse_optimizer.cpp:206-267,166-190)
     int initialize() {
-        std::vector<uint8_t> pAct(D.nKF, 0);
+        std::vector<int> pAct(D.nKF + 1, 0);   // [nKF] = this rank has an active edge
         std::fill(ptAct.begin(), ptAct.end(), 0);
         const int* eMP = h_eMP; const int* eKF = h_eKF;
-        for (int e = 0; e < D.nE; e++) if (level[e] == 0) { pAct[eKF[e]] = 1; ptAct[eMP[e]] = 1; }
+        nActive = 0;
+        for (int e = 0; e < D.nE; e++) if (level[e] == 0) { pAct[eKF[e]] = 1; ptAct[eMP[e]] = 1; nActive++; }
+        pAct[D.nKF] = nActive > 0;
+        if (o->nranks > 1) {   // a rank sees the edges of its own landmarks only: pose activity and "anything to optimize" are global facts
+            CSLAM_CUDA(cudaMemcpyAsync(d_pact, pAct.data(), (D.nKF + 1) * sizeof(int), cudaMemcpyHostToDevice, o->stream));
+            int rc = nccl_api()->AllReduce(d_pact, d_pact, D.nKF + 1, NCCL_I32, NCCL_MAX, o->comm, o->stream);
+            if (rc) { set_error("ncclAllReduce (pose activity) failed (%d)", rc); return CSLAM_E_NCCL; }
+            CSLAM_CUDA(cudaMemcpyAsync(pAct.data(), d_pact, (D.nKF + 1) * sizeof(int), cudaMemcpyDeviceToHost, o->stream));
+            CSLAM_CUDA(cudaStreamSynchronize(o->stream));
+            nActive = pAct[D.nKF];   // only tested against zero
+        }
         int nP = 0;
         for (int k = 0; k < D.nKF; k++) poseIdx[k] = (pAct[k] && !fixed[k]) ? nP++ : -1;
         D.nP = nP; D.n = 6 * nP;
         CSLAM_CUDA(cudaMemcpyAsync(d_poseIdx, poseIdx.data(), D.nKF * sizeof(int), cudaMemcpyHostToDevice, o->stream));
         CSLAM_CUDA(cudaMemcpyAsync(d_ptAct, ptAct.data(), D.nMP, cudaMemcpyHostToDevice, o->stream));
         CSLAM_CUDA(cudaMemcpyAsync(D.level, level.data(), D.nE, cudaMemcpyHostToDevice, o->stream));
-        nActive = 0; for (int e = 0; e < D.nE; e++) nActive += level[e] == 0;
+        errorsCurrent = false;   // level / robust kernel changed
         bind();
         drop_graph();   // the captured trial bakes in nP / n / the level array's meaning
         return 0;
@@ -1034,7 +1088,7 @@ struct BAHost {
     int errors_chi2(double* chi) {   // computeActiveErrors + activeRobustChi2
         k_ba_errors<<<grid(D.nE), 256, 0, o->stream>>>(D, D.scal); o->launches++;
         int rc;
-        if ((rc = allreduce(D.scal, 1, NCCL_SUM))) return rc;
+        if ((rc = allreduce_small(D.scal, 1, false))) return rc;
         if ((rc = fetch(D.scal, 1))) return rc;
         *chi = o->h_scal[0];
         return 0;
@@ -1056,7 +1110,7 @@ struct BAHost {
             M.Hpp = HppFull;
         }
         k_ba_maxdiag<<<grid(D.nP * 6 + D.nMP * 3), 256, 0, o->stream>>>(M); o->launches++;
-        if ((rc = allreduce(D.scal + 2, 1, NCCL_MAX))) return rc;
+        if ((rc = allreduce_small(D.scal + 2, 1, true))) return rc;
         if ((rc = fetch(D.scal, 4))) return rc;
         *lam = 1e-5 * o->h_scal[2];
         return 0;
@@ -1124,7 +1178,7 @@ struct BAHost {
         tick(BK_SCALE);
         k_ba_scale<<<grid(D.n + 3 * D.nMP), 256, 0, o->stream>>>(SV, D.scal + 1); o->launches++;
         tick(BK_END);
-        if ((rc = allreduce(D.scal, 2, NCCL_SUM))) return rc;
+        if ((rc = allreduce_small(D.scal, 2, false))) return rc;
         CSLAM_CUDA(cudaMemcpyAsync(o->h_scal, D.scal, 4 * sizeof(double), cudaMemcpyDeviceToHost, o->stream));
         CSLAM_CUDA(cudaGetLastError());
         return 0;
@@ -1161,7 +1215,10 @@ struct BAHost {
     int lm_iteration(int iteration, int* result) {
         int rc; double currentChi = 0;
         tick(BK_ERRORS);
-        if ((rc = errors_chi2(&currentChi))) return rc;
+        // computeActiveErrors + activeRobustChi2: after an accepted trial the errors and chi2 of this very state are already on the device
+        // (the trial evaluated them; same kernel, same inputs -> same bits), so only the first iteration and the ones after a rejection compute
+        if (errorsCurrent) currentChi = lastChi;
+        else if ((rc = errors_chi2(&currentChi))) return rc;
         const double iniChi = currentChi; double tempChi = currentChi;
         tick(BK_LIN_POINTS);
         if ((rc = build_system())) return rc;
@@ -1181,7 +1238,9 @@ struct BAHost {
                 double alpha = 1. - std::pow((2 * rho - 1), 3);
                 alpha = std::min(alpha, 2. / 3.);
                 lambda *= std::max(1. / 3., alpha); ni = 2; currentChi = tempChi; accepted = 1;
+                errorsCurrent = true; lastChi = tempChi;
             } else {
+                errorsCurrent = false;   // pop(): the state is the old one again, the error array holds the trial's
                 lambda *= ni; ni *= 2;
                 k_ba_restore<<<grid(std::max(D.nKF, D.nMP)), 256, 0, o->stream>>>(D); o->launches++;
                 if (!ok2) rho = -1;
@@ -1210,19 +1269,11 @@ struct BAHost {
         }
         return 0;
     }
-    int classify(std::vector<uint8_t>& flags) {
+    int classify(std::vector<uint8_t>& flags) {   // flags of this rank's edges (all edges on one GPU)
         k_ba_classify<<<grid(D.nE), 256, 0, o->stream>>>(D, d_flag); o->launches++;
         flags.resize(D.nE);
         CSLAM_CUDA(cudaMemcpyAsync(flags.data(), d_flag, D.nE, cudaMemcpyDeviceToHost, o->stream));
         CSLAM_CUDA(cudaStreamSynchronize(o->stream));
-        if (o->nranks > 1) {   // a rank only holds valid errors / points for the edges of its own landmarks: keep the owners' flags (max over ranks)
-            for (int s = 0; s < D.nE; s++) if ((h_eMP[s] % o->nranks) != o->rank) flags[s] = 0;
-            CSLAM_CUDA(cudaMemcpyAsync(d_flag, flags.data(), D.nE, cudaMemcpyHostToDevice, o->stream));
-            int rc = nccl_api()->AllReduce(d_flag, d_flag, D.nE, NCCL_U8, NCCL_MAX, o->comm, o->stream);
-            if (rc) { set_error("ncclAllReduce (flags) failed (%d)", rc); return CSLAM_E_NCCL; }
-            CSLAM_CUDA(cudaMemcpyAsync(flags.data(), d_flag, D.nE, cudaMemcpyDeviceToHost, o->stream));
-            CSLAM_CUDA(cudaStreamSynchronize(o->stream));
-        }
         return 0;
     }
 };
@@ -1248,29 +1299,36 @@ extern "C" int cslam_local_ba(cslam_optimizer* o, cslam_ba_problem* p, const vol
     auto tNow = []() { return std::chrono::steady_clock::now(); };
     auto tMs = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) { return std::chrono::duration<double, std::milli>(b - a).count(); };
     const auto tp0 = tNow();
-    const int nKF = p->n_kf, nMP = p->n_mp, nE = p->n_edges;
-    if (r) { r->iterations = 0; r->trials = 0; if (r->outlier) std::memset(r->outlier, 0, nE); }
+    const int nKF = p->n_kf, nMP = p->n_mp, nEg = p->n_edges;   // nEg: the caller's edges; nE below: the edges this rank works on
+    if (r) { r->iterations = 0; r->trials = 0; if (r->outlier) std::memset(r->outlier, 0, nEg); }
     if (stop_flag && *stop_flag) return CSLAM_OK;   // src/Optimizer.cpp:359-361
     BAHost H; H.o = o; H.res = r; H.stop = stop_flag;
     BADev& D = H.D; std::memset(&D, 0, sizeof(D));
-    D.nKF = nKF; D.nMP = nMP; D.nE = nE; D.f = p->face_w / 2.0; D.rank = o->rank; D.nranks = o->nranks;
+    D.nKF = nKF; D.nMP = nMP; D.f = p->face_w / 2.0; D.rank = o->rank; D.nranks = o->nranks;
     const float dlt = (float)std::sqrt(5.991); D.delta = (double)dlt; D.dsqr = D.delta * D.delta; D.robust = 1;
     // ---- edges sorted by landmark (stable), CSR by landmark and by keyframe. Host work is two passes over the endpoint arrays (in scratch
     // vectors that live in the optimizer object: no page faults per call); the per-edge float work happens on the device (k_ba_prep_edges).
     cslam_optimizer::HostScratch& hs = o->hs;
     hs.lmStart.assign(nMP + 1, 0);
-    bool grouped = true;
-    for (int e = 0; e < nE; e++) {
+    // Multi-GPU: landmark l (with all its edges) belongs to rank l % nranks; a rank works on the edges of its own landmarks ONLY, so every
+    // per-edge kernel, the co-observation lists and the Schur work shrink by 1 / nranks; the reduced camera system is what gets exchanged.
+    const bool multi = o->nranks > 1;
+    bool grouped = !multi;
+    int nLocal = 0;
+    for (int e = 0; e < nEg; e++) {
         const int l = p->edge_mp[e], k = p->edge_kf[e];
         if (l < 0 || l >= nMP || k < 0 || k >= nKF) { set_error("edge %d references a vertex out of range", e); return CSLAM_E_BADARG; }
-        hs.lmStart[l + 1]++;
+        if (multi && (l % o->nranks) != o->rank) continue;
+        hs.lmStart[l + 1]++; nLocal++;
         if (e && l < p->edge_mp[e - 1]) grouped = false;
     }
+    const int nE = nLocal;
+    D.nE = nE;
     for (int l = 0; l < nMP; l++) hs.lmStart[l + 1] += hs.lmStart[l];
     if (grouped) { H.perm = nullptr; H.h_eMP = p->edge_mp; H.h_eKF = p->edge_kf; }
     else {
         hs.perm.resize(nE); hs.eMP.resize(nE); hs.eKF.resize(nE); hs.fill.assign(hs.lmStart.begin(), hs.lmStart.end() - 1);
-        for (int e = 0; e < nE; e++) hs.perm[hs.fill[p->edge_mp[e]]++] = e;
+        for (int e = 0; e < nEg; e++) { const int l = p->edge_mp[e]; if (!multi || (l % o->nranks) == o->rank) hs.perm[hs.fill[l]++] = e; }
         for (int s = 0; s < nE; s++) { const int e = hs.perm[s]; hs.eMP[s] = p->edge_mp[e]; hs.eKF[s] = p->edge_kf[e]; }
         H.perm = hs.perm.data(); H.h_eMP = hs.eMP.data(); H.h_eKF = hs.eKF.data();
     }
@@ -1293,14 +1351,14 @@ extern "C" int cslam_local_ba(cslam_optimizer* o, cslam_ba_problem* p, const vol
     int* d_eMP = nullptr; int* d_eKF = nullptr; int* d_perm = nullptr; float2* d_kp = nullptr; float* d_isig = nullptr; float* d_pts32 = nullptr; int* d_bad = nullptr;
     double* d_obs = nullptr; int8_t* d_face = nullptr;
     if ((rc = dupload(o, &cpose, poses)) || (rc = dupload(o, &D.lmStart, hs.lmStart)) || (rc = dupload(o, &D.peStart, hs.peStart)) || (rc = dupload(o, &D.peList, hs.peList)) ||
-        (rc = dupload(o, &D.kfOfQ, kfOfQ)) || (rc = dalloc(o, &d_eMP, nE)) || (rc = dalloc(o, &d_eKF, nE)) || (rc = dalloc(o, &d_kp, nE)) || (rc = dalloc(o, &d_isig, nE)) ||
+        (rc = dupload(o, &D.kfOfQ, kfOfQ)) || (rc = dalloc(o, &d_eMP, nE)) || (rc = dalloc(o, &d_eKF, nE)) || (rc = dalloc(o, &d_kp, nEg)) || (rc = dalloc(o, &d_isig, nEg)) ||
         (rc = dalloc(o, &d_pts32, (size_t)nMP * 3)) || (rc = dalloc(o, &cX, (size_t)nMP * 3)) || (rc = dalloc(o, &d_obs, (size_t)nE * 3)) || (rc = dalloc(o, &d_face, nE)) ||
         (rc = dalloc(o, &d_bad, 1)) || (!grouped && (rc = dalloc(o, &d_perm, nE)))) return rc;
     if (nE > 0) {
         CSLAM_CUDA(cudaMemcpyAsync(d_eMP, H.h_eMP, (size_t)nE * 4, cudaMemcpyHostToDevice, o->stream));
         CSLAM_CUDA(cudaMemcpyAsync(d_eKF, H.h_eKF, (size_t)nE * 4, cudaMemcpyHostToDevice, o->stream));
-        CSLAM_CUDA(cudaMemcpyAsync(d_kp, p->kp_xy, (size_t)nE * 8, cudaMemcpyHostToDevice, o->stream));
-        CSLAM_CUDA(cudaMemcpyAsync(d_isig, p->inv_sigma2, (size_t)nE * 4, cudaMemcpyHostToDevice, o->stream));
+        CSLAM_CUDA(cudaMemcpyAsync(d_kp, p->kp_xy, (size_t)nEg * 8, cudaMemcpyHostToDevice, o->stream));
+        CSLAM_CUDA(cudaMemcpyAsync(d_isig, p->inv_sigma2, (size_t)nEg * 4, cudaMemcpyHostToDevice, o->stream));
         if (!grouped) CSLAM_CUDA(cudaMemcpyAsync(d_perm, H.perm, (size_t)nE * 4, cudaMemcpyHostToDevice, o->stream));
     }
     if (nMP > 0) CSLAM_CUDA(cudaMemcpyAsync(d_pts32, p->points, (size_t)nMP * 12, cudaMemcpyHostToDevice, o->stream));
@@ -1314,7 +1372,7 @@ extern "C" int cslam_local_ba(cslam_optimizer* o, cslam_ba_problem* p, const vol
     const int maxBlocks = std::max({cdiv(nE, 256), cdiv(nmax + 3 * nMP, 256), 1});
     long long* pairCnt = nullptr;
     if ((rc = dalloc(o, &D.poseBak, nKF)) || (rc = dalloc(o, &D.Xbak, (size_t)nMP * 3)) || (rc = dalloc(o, &D.err, (size_t)nE * 2, true)) || (rc = dalloc(o, &D.level, nE, true)) ||
-        (rc = dalloc(o, &H.d_poseIdx, nKF)) || (rc = dalloc(o, &H.d_ptAct, nMP)) || (rc = dalloc(o, &H.d_flag, nE)) || (rc = dalloc(o, &D.Hpp, (size_t)std::max(nQ, 1) * 36)) ||
+        (rc = dalloc(o, &H.d_poseIdx, nKF)) || (rc = dalloc(o, &H.d_pact, nKF + 1)) || (rc = dalloc(o, &H.d_ptAct, nMP)) || (rc = dalloc(o, &H.d_flag, nE)) || (rc = dalloc(o, &D.Hpp, (size_t)std::max(nQ, 1) * 36)) ||
         (rc = dalloc(o, &D.bp, (size_t)std::max(nQ, 1) * 6)) || (rc = dalloc(o, &D.Hll, (size_t)nMP * 9)) || (rc = dalloc(o, &D.bl, (size_t)nMP * 3)) ||
         (rc = dalloc(o, &D.Hpl, (size_t)nE * 18)) || (rc = dalloc(o, &D.Dinv, (size_t)nMP * DINV_LD)) || (rc = dalloc(o, &D.db, (size_t)nMP * 3)) ||
         (rc = dalloc(o, &H.red, payloadMax)) || (rc = dalloc(o, &D.xp, std::max(nmax, 1), true)) || (rc = dalloc(o, &D.xl, (size_t)nMP * 3, true)) ||
@@ -1342,7 +1400,7 @@ extern "C" int cslam_local_ba(cslam_optimizer* o, cslam_ba_problem* p, const vol
         CSLAM_CUDA(cudaMemcpyAsync(&total, pairCnt + (size_t)nQ * nQ, sizeof(long long), cudaMemcpyDeviceToHost, o->stream));
         CSLAM_CUDA(cudaMemcpyAsync(&badEdge, d_bad, sizeof(int), cudaMemcpyDeviceToHost, o->stream));
         CSLAM_CUDA(cudaStreamSynchronize(o->stream));
-        if (badEdge < nE) { set_error("edge %d: keypoint (%g,%g) is on no cube face (the reference calls exit() here)", badEdge, p->kp_xy[2 * badEdge], p->kp_xy[2 * badEdge + 1]); return CSLAM_E_BADARG; }
+        if (badEdge < nEg) { set_error("edge %d: keypoint (%g,%g) is on no cube face (the reference calls exit() here)", badEdge, p->kp_xy[2 * badEdge], p->kp_xy[2 * badEdge + 1]); return CSLAM_E_BADARG; }
         int2* tuples = nullptr;
         if ((rc = dalloc(o, &tuples, (size_t)std::max<long long>(total, 1)))) return rc;
         k_ba_pairs_fill<<<dim3(nQ, nQ), 128, 0, o->stream>>>(D, pairCnt, tuples); o->launches++;
@@ -1352,7 +1410,7 @@ extern "C" int cslam_local_ba(cslam_optimizer* o, cslam_ba_problem* p, const vol
     if (nQ == 0) {
         CSLAM_CUDA(cudaMemcpyAsync(&badEdge, d_bad, sizeof(int), cudaMemcpyDeviceToHost, o->stream));
         CSLAM_CUDA(cudaStreamSynchronize(o->stream));
-        if (badEdge < nE) { set_error("edge %d: keypoint (%g,%g) is on no cube face (the reference calls exit() here)", badEdge, p->kp_xy[2 * badEdge], p->kp_xy[2 * badEdge + 1]); return CSLAM_E_BADARG; }
+        if (badEdge < nEg) { set_error("edge %d: keypoint (%g,%g) is on no cube face (the reference calls exit() here)", badEdge, p->kp_xy[2 * badEdge], p->kp_xy[2 * badEdge + 1]); return CSLAM_E_BADARG; }
     }
     if (hostProf) cudaStreamSynchronize(o->stream);
     const auto tp2 = tNow();
@@ -1368,6 +1426,17 @@ extern "C" int cslam_local_ba(cslam_optimizer* o, cslam_ba_problem* p, const vol
         if ((rc = H.optimize(its2))) return rc;
     }
     if ((rc = H.classify(flags))) return rc;
+    std::vector<uint8_t> gflags;   // multi-GPU: every rank returns the flags of ALL edges (max over the owners' flags, in the caller's order)
+    if (multi) {
+        uint8_t* d_gflag = nullptr;
+        if ((rc = dalloc(o, &d_gflag, std::max(nEg, 1), true))) return rc;
+        if (nE > 0) { k_ba_scatter_flags<<<cdiv(nE, 256), 256, 0, o->stream>>>(nE, d_perm, H.d_flag, d_gflag); o->launches++; }
+        rc = nccl_api()->AllReduce(d_gflag, d_gflag, nEg, NCCL_U8, NCCL_MAX, o->comm, o->stream);
+        if (rc) { set_error("ncclAllReduce (flags) failed (%d)", rc); return CSLAM_E_NCCL; }
+        gflags.resize(nEg);
+        CSLAM_CUDA(cudaMemcpyAsync(gflags.data(), d_gflag, nEg, cudaMemcpyDeviceToHost, o->stream));
+        CSLAM_CUDA(cudaStreamSynchronize(o->stream));
+    }
     const auto tp3 = tNow();
     H.drop_graph();
     if (H.d_prof) {
@@ -1391,7 +1460,7 @@ extern "C" int cslam_local_ba(cslam_optimizer* o, cslam_ba_problem* p, const vol
     }
     for (size_t i = 0; i < X.size(); i++) { p->points[i] = (float)X[i]; if (r && r->points_fp64) r->points_fp64[i] = X[i]; }
     if (r) {
-        if (r->outlier) for (int s = 0; s < nE; s++) r->outlier[H.perm ? H.perm[s] : s] = flags[s];
+        if (r->outlier) { if (multi) std::memcpy(r->outlier, gflags.data(), nEg); else for (int s = 0; s < nE; s++) r->outlier[H.perm ? H.perm[s] : s] = flags[s]; }
         r->iterations = H.iterations; r->trials = H.trials;
     }
     free_pool(o);

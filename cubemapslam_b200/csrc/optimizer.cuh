@@ -24,7 +24,7 @@ struct cslam_optimizer {
     bool timing = false; std::vector<cudaEvent_t> ev; std::vector<int> evKind; int evUsed = 0; double kindMs[16] = {0}; int64_t kindCount[16] = {0};
     // one-shot NVLink all-reduce of the reduced camera system (multi-GPU LocalBA): peer views of every rank's exchange buffer
     struct Peer { void* base = nullptr; bool mine = false; };
-    std::vector<Peer> peers; size_t xchgBytes = 0; uint32_t epoch = 0; bool oneShot = false;
+    std::vector<Peer> peers; size_t xchgBytes = 0; uint32_t epoch = 0, epoch2 = 0; bool oneShot = false;
 };
 
 namespace cslam {

@@ -13,7 +13,10 @@ rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE"
 torch.cuda.set_device(local)
 dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 small = len(sys.argv) > 1 and sys.argv[1] == "small"
-p = synth.ba_problem(nKF=12, nMP=1500, kmin=2, kmax=8, faceW=450, seed=3, radius=1.5) if small else synth.ba_problem()
+dense = len(sys.argv) > 1 and sys.argv[1] == "dense"
+prof = "prof" in sys.argv[1:]
+p = (synth.ba_problem(nKF=12, nMP=1500, kmin=2, kmax=8, faceW=450, seed=3, radius=1.5) if small else
+     synth.ba_problem(nKF=50, nMP=4000, kmin=50, kmax=50, radius=9.0) if dense else synth.ba_problem())
 W = p["faceW"]
 args = (p["Tcw"], p["kf_fixed"], p["pts"], p["eMP"], p["eKF"], p["kpxy"], p["inv_sigma2"], W, W)
 o = Optimizer(device=local)
@@ -29,6 +32,15 @@ g = o.LocalBundleAdjustment(*args)
 torch.cuda.synchronize(); dist.barrier()
 dt = time.perf_counter() - t0
 tt = torch.tensor([dt], dtype=torch.float64, device="cuda"); dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+if prof:   # per-kernel CUDA-event timing of one more call (every rank takes part; rank 0 prints)
+    o.set_timing(True)
+    o.LocalBundleAdjustment(*args)
+    tm = o.timing(); o.set_timing(False)
+    if rank == 0:
+        tot = sum(v[0] for v in tm.values())
+        for k, (ms, cnt) in sorted(tm.items(), key=lambda kv: -kv[1][0]):
+            print(f"  {k:16s} {1e3 * ms / max(cnt, 1):8.1f} us avg over {cnt:3d}  ({100 * ms / tot:4.1f}%)", file=sys.stderr)
+        print(f"  GPU time per LM trial (events), rank 0 of {world}: {1e3 * tot / max(g['trials'] if 'trials' in g else g['iters'], 1):.1f} us", file=sys.stderr)
 if rank == 0:
     ref = Optimizer(device=local)
     r = ref.LocalBundleAdjustment(*args)
