@@ -48,7 +48,7 @@ struct BADev {
     const int* lmStart;              // nMP+1, CSR over sorted edges
     const int* peStart; const int* peList;      // CSR of sorted edge ids by KF (ascending = landmark order)
     const long long* pairStart;      // nQ*nQ+1: co-observation list of (q1,q2), q1<=q2, row-major
-    const int2* tuples;              // (a1, a2)
+    const int4* tuples;              // (a1, a2, landmark, -): the landmark rides along so that k_ba_schur has no tuple -> edge -> landmark load chain
     double *Hpp, *bp, *Hll, *bl, *Hpl, *Dinv, *db, *xp, *xl;
     double *S, *g, *bpr, *tail;      // one contiguous exchange buffer: [S n*n | g n | bpr n | tail 4]; tail = chi2, scale, -, -
     double* scal;                    // [0] chi2, [1] scale, [2] max diag (as bits), [3] solve flag, [4] lambda of the current trial
@@ -315,14 +315,14 @@ __global__ void __launch_bounds__(1024) k_ba_pairs_scan(long long* v, int m) {
     }
     if (threadIdx.x == 0) v[m] = carry;
 }
-__global__ void __launch_bounds__(128) k_ba_pairs_fill(BADev D, const long long* start, int2* tuples) {
+__global__ void __launch_bounds__(128) k_ba_pairs_fill(BADev D, const long long* start, int4* tuples) {
     __shared__ int wcnt[4];
     __shared__ long long base;
     const int q1 = blockIdx.y, q2 = blockIdx.x;
     if (q1 > q2) return;
     const int k1 = D.kfOfQ[q1], k2 = D.kfOfQ[q2], beg = D.peStart[k1], end = D.peStart[k1 + 1];
-    int2* out = tuples + start[(size_t)q1 * D.nQ + q2];
-    if (q1 == q2) { for (int q = beg + threadIdx.x; q < end; q += blockDim.x) { const int a = D.peList[q]; out[q - beg] = make_int2(a, a); } return; }
+    int4* out = tuples + start[(size_t)q1 * D.nQ + q2];
+    if (q1 == q2) { for (int q = beg + threadIdx.x; q < end; q += blockDim.x) { const int a = D.peList[q]; out[q - beg] = make_int4(a, a, D.eMP[a], 0); } return; }
     if (threadIdx.x == 0) base = 0;
     __syncthreads();
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
@@ -335,7 +335,7 @@ __global__ void __launch_bounds__(128) k_ba_pairs_fill(BADev D, const long long*
         __syncthreads();
         int pre = 0;
         for (int ww = 0; ww < w; ww++) pre += wcnt[ww];
-        if (a2 >= 0) out[base + pre + __popc(ball & ((1u << lane) - 1))] = make_int2(a1, a2);
+        if (a2 >= 0) out[base + pre + __popc(ball & ((1u << lane) - 1))] = make_int4(a1, a2, D.eMP[a1], 0);
         __syncthreads();
         if (threadIdx.x == 0) base += wcnt[0] + wcnt[1] + wcnt[2] + wcnt[3];
         __syncthreads();
@@ -360,9 +360,12 @@ __global__ void __launch_bounds__(SCHUR_T) k_ba_schur(BADev D, int addLambda) {
 #pragma unroll
     for (int i = 0; i < 21; i++) acc[i] = 0.0;
     const long long beg = D.pairStart[(size_t)q1 * D.nQ + q2], end = D.pairStart[(size_t)q1 * D.nQ + q2 + 1];
-    for (long long t = beg + (threadIdx.x >> 1); t < end; t += SCHUR_T / 2) {
-        const int2 tp = D.tuples[t];
-        const int l = D.eMP[tp.x];
+    long long t = beg + (threadIdx.x >> 1);
+    int4 nxt = t < end ? D.tuples[t] : make_int4(0, 0, 0, 0);
+    for (; t < end; t += SCHUR_T / 2) {
+        const int4 tp = nxt;
+        if (t + SCHUR_T / 2 < end) nxt = D.tuples[t + SCHUR_T / 2];   // the next tuple's index load flies under this tuple's block loads
+        const int l = tp.z;
         if (!owned(D, l)) continue;
         // 19 128-bit loads per thread: every lane reads a different block, so the L1 wavefront count per byte is what bounds this kernel
         const double2* B1v = reinterpret_cast<const double2*>(D.Hpl + 18 * (size_t)tp.x) + 4 * h;   // doubles 8h .. 8h+9: rows 3h..3h+2 are w[h .. h+8]
@@ -1401,7 +1404,7 @@ extern "C" int cslam_local_ba(cslam_optimizer* o, cslam_ba_problem* p, const vol
         CSLAM_CUDA(cudaMemcpyAsync(&badEdge, d_bad, sizeof(int), cudaMemcpyDeviceToHost, o->stream));
         CSLAM_CUDA(cudaStreamSynchronize(o->stream));
         if (badEdge < nEg) { set_error("edge %d: keypoint (%g,%g) is on no cube face (the reference calls exit() here)", badEdge, p->kp_xy[2 * badEdge], p->kp_xy[2 * badEdge + 1]); return CSLAM_E_BADARG; }
-        int2* tuples = nullptr;
+        int4* tuples = nullptr;
         if ((rc = dalloc(o, &tuples, (size_t)std::max<long long>(total, 1)))) return rc;
         k_ba_pairs_fill<<<dim3(nQ, nQ), 128, 0, o->stream>>>(D, pairCnt, tuples); o->launches++;
         CSLAM_CUDA(cudaGetLastError());

@@ -411,6 +411,44 @@ extern "C" int cslam_ubench_popc(cslam_matcher* m, double* popc32_per_s) {
     return CSLAM_OK;
 }
 
+// The front end's k_fast is bound by the issue rate of 3-input u16x2 min / max (VIMNMX3.U16x2, 80 of them per pixel pair): the same kind of
+// register-only chain measurement gives the denominator of its roofline.
+__global__ void __launch_bounds__(256) k_ubench_minmax3(uint32_t* out, int iters, uint32_t seed) {
+    uint32_t a[8], acc[8];
+#pragma unroll
+    for (int k = 0; k < 8; k++) { a[k] = (seed * (threadIdx.x + 1) + k * 0x9e3779b9u + blockIdx.x) & 0x00ff00ffu; acc[k] = a[k] ^ 0x00550055u; }
+    for (int i = 0; i < iters; i += 2) {
+#pragma unroll
+        for (int k = 0; k < 8; k++) acc[k] = __vimin3_u16x2(acc[k] + 0x00010001u * (i & 1), a[k], acc[(k + 1) & 7]);
+#pragma unroll
+        for (int k = 0; k < 8; k++) acc[k] = __vimax3_u16x2(acc[k], a[(k + 3) & 7], acc[(k + 5) & 7]);
+    }
+    uint32_t s = 0;
+#pragma unroll
+    for (int k = 0; k < 8; k++) s += acc[k];
+    if (s == 0xdeadbeefu) out[0] = s;
+}
+extern "C" int cslam_ubench_minmax3(cslam_matcher* m, double* ops_per_s) {
+    if (!m || !ops_per_s) return CSLAM_E_BADARG;
+    CSLAM_CUDA(cudaSetDevice(m->device));
+    int sms = 148;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, m->device);
+    const int blocks = sms * 8, iters = 20000;
+    cudaEvent_t e0, e1;
+    CSLAM_CUDA(cudaEventCreate(&e0)); CSLAM_CUDA(cudaEventCreate(&e1));
+    k_ubench_minmax3<<<blocks, 256, 0, m->stream>>>(reinterpret_cast<uint32_t*>(m->dN), 100, 1u);   // warm-up
+    CSLAM_CUDA(cudaEventRecord(e0, m->stream));
+    k_ubench_minmax3<<<blocks, 256, 0, m->stream>>>(reinterpret_cast<uint32_t*>(m->dN), iters, 1u);
+    CSLAM_CUDA(cudaEventRecord(e1, m->stream));
+    CSLAM_CUDA(cudaStreamSynchronize(m->stream));
+    float ms = 0;
+    CSLAM_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    m->launches += 2;
+    *ops_per_s = (double)blocks * 256.0 * iters * 8.0 / (ms * 1e-3);   // warp-lane u16x2 3-input min/max per second
+    return CSLAM_OK;
+}
+
 static int pow2_at_least(int n) { int p = 1; while (p < n) p <<= 1; return p; }
 
 extern "C" int cslam_search_by_bow_dev(cslam_matcher* m, const uint8_t* descKF, const float* angKF, const uint8_t* kf_valid, const int32_t* node_kf, int nKF,

@@ -88,6 +88,11 @@ class ORBMatcher:
         check(lib().cslam_ubench_popc(self._h, C.byref(v)))
         return v.value
 
+    def ubench_minmax3(self):
+        v = C.c_double()
+        check(lib().cslam_ubench_minmax3(self._h, C.byref(v)))
+        return v.value
+
     def SearchByBoW(self, descKF, angKF, kf_valid, node_kf, descF, angF, node_f):
         a = [np.ascontiguousarray(descKF, np.uint8), np.ascontiguousarray(angKF, np.float32), np.ascontiguousarray(kf_valid, np.uint8),
              np.ascontiguousarray(node_kf, np.int32), np.ascontiguousarray(descF, np.uint8), np.ascontiguousarray(angF, np.float32),

@@ -121,6 +121,8 @@ int cslam_match_frames(cslam_matcher* m, const cslam_keypoint* kps, const uint8_
 /* Measured POPC issue rate of this GPU (32-bit population counts per second with the XOR+POPC+ADD mix of the Hamming kernels, no memory traffic):
  * the ceiling the matcher's roofline fraction is quoted against (bench.py). */
 int cslam_ubench_popc(cslam_matcher* m, double* popc32_per_s);
+/* Same for 3-input u16x2 min/max (VIMNMX3.U16x2), the instruction k_fast is bound by; out: thread-level operations per second. */
+int cslam_ubench_minmax3(cslam_matcher* m, double* ops_per_s);
 /* ORBMatcher::SearchByBoW(KeyFrame*, Frame&, vector<MapPoint*>&) (src/ORBMatcher.cpp:409-539) for npairs (KF,F) pairs.
  * kf_valid: 1 where the KF feature has a good MapPoint; node_kf/node_f: DBoW2 FeatureVector node id per feature.
  * match_f: npairs x nF (index of the KF feature whose MapPoint is assigned, or -1); nmatches: npairs. */
