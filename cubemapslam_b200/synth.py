@@ -230,6 +230,29 @@ def tracking_pair(seed=0, n=2000, faceW=650, motion=0.02, rot=0.01, mp_frac=0.8,
     return dict(kLast=kL, dLast=dL, TcwLast=TcwL, hasMP=hasMP, Xw=Xw, mpObs=mpObs, kCur=kC, dCur=dC, TcwCur=TcwC, src=src, scale=scale, curTaken=curTaken, faceW=W)
 
 
+def mapping_pair(seed=0, n=1500, faceW=650):
+    """Two key frames for the LocalMapping feature operations (Fuse, SearchForTriangulation), built on tracking_pair: KF "obs" = its LastFrame
+    (identity pose, MapPoint m seen by key point m), KF "cur" = its CurrentFrame. Adds vocabulary-node ids shared by true correspondences, MapPoint
+    presence flags and the essential matrix E12 (x_cur^T E12 x_obs = 0 for bearing vectors), float32 like the reference's cv::Mat."""
+    s = tracking_pair(100 + seed, n=n, faceW=faceW, motion=0.25, rot=0.03)
+    rng = np.random.default_rng(9000 + seed)
+    nO, nC = len(s["kLast"]), len(s["kCur"])
+    nodeO = rng.integers(0, 120, nO).astype(np.int32)
+    nodeC = np.where(s["src"] >= 0, nodeO[np.maximum(s["src"], 0)], rng.integers(0, 120, nC)).astype(np.int32)
+    flip = rng.random(nC) < 0.1
+    nodeC[flip] = rng.integers(0, 120, int(flip.sum()))
+    T1 = s["TcwCur"].astype(np.float64); T2 = s["TcwLast"].astype(np.float64)     # KF1 = cur, KF2 = obs
+    R1, t1, R2, t2 = T1[:3, :3], T1[:3, 3], T2[:3, :3], T2[:3, 3]
+    R12 = R1 @ R2.T; t12 = -R12 @ t2 + t1
+    tx = np.array([[0, -t12[2], t12[1]], [t12[2], 0, -t12[0]], [-t12[1], t12[0], 0]])
+    E12 = (tx @ R12).astype(np.float32)
+    level_sigma2 = (s["scale"] * s["scale"]).astype(np.float32)
+    inv_level_sigma2 = (np.float32(1.0) / level_sigma2).astype(np.float32)
+    s.update(nodeObs=nodeO, nodeCur=nodeC, hasMPCur=(rng.random(nC) < 0.4).astype(np.uint8), hasMPObs=(rng.random(nO) < 0.4).astype(np.uint8), E12=E12,
+             level_sigma2=level_sigma2, inv_level_sigma2=inv_level_sigma2)
+    return s
+
+
 # ----------------------------------------------------------------------------- vocabulary tree (DBoW2 text format)
 def vocabulary(k=10, L=4, seed=0, stop_frac=0.01):
     """A synthetic vocabulary tree in ORBvoc.txt's node order (breadth-first per parent, like DBoW2's saveToTextFile): arrays for nodes 1..n

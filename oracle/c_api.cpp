@@ -8,6 +8,7 @@
 #include "bow.h"
 #include "cvprim.h"
 #include "frame_index.h"
+#include "mapping.h"
 #include "orb_extractor.h"
 #include "orb_matcher.h"
 
@@ -197,6 +198,22 @@ int orc_search_by_projection_local(void* hv, const uint8_t* dF, const float* sca
     GridHandle* h = (GridHandle*)hv;
     return fi_search_by_projection_local(h->g, h->kps.data(), dF, (int)h->kps.size(), scaleFactors, nMP, inView, projXY, level, viewCos, dMP, mpObs, fTaken, th, nnratio, matchF);
 }
+// ---- LocalMapping feature operations (mapping.h)
+void orc_distinctive_descriptors(const uint8_t* desc, const int* offset, int nPoints, int* best) {
+    for (int p = 0; p < nPoints; p++) best[p] = distinctive_descriptor(desc + 32 * (size_t)offset[p], offset[p + 1] - offset[p]);
+}
+void orc_fuse_search(void* hv, const uint8_t* dKF, const float* Tcw, const float* scaleFactors, const float* invLevelSigma2, int nMP, const uint8_t* valid, const float* Xw,
+                     const int* level, const uint8_t* dMP, float th, int* bestIdx, int* bestDist) {
+    GridHandle* h = (GridHandle*)hv;
+    fuse_search(h->g, h->kps.data(), dKF, Tcw, scaleFactors, invLevelSigma2, nMP, valid, Xw, level, dMP, th, bestIdx, bestDist);
+}
+int orc_search_for_triangulation(const KeyPoint* k1, const uint8_t* d1, const float* rays1, const uint8_t* hasMP1, const int* node1, int n1, const KeyPoint* k2, const uint8_t* d2,
+                                 const float* rays2, const uint8_t* hasMP2, const int* node2, int n2, const float* Ow1, const float* Tcw2, const float* E12,
+                                 const float* scaleFactors, const float* levelSigma2, int faceW, int faceH, int checkOri, int* match12) {
+    return search_for_triangulation(k1, d1, rays1, hasMP1, node1, n1, k2, d2, rays2, hasMP2, node2, n2, Ow1, Tcw2, E12, scaleFactors, levelSigma2, faceW, faceH, checkOri != 0, match12);
+}
+float orc_vector_sigma(float kx, float ky, const float* normalRig, int faceW, int faceH) { return vector_sigma(kx, ky, normalRig, faceW, faceH); }
+
 int orc_area_rects(float x, float y, float r, int faceW, int faceH, int* rects) {
     FiRect rc[3]; const float inv = static_cast<float>(3 * FI_G) / static_cast<float>((float)(3 * faceW) - 0.0f);
     const int n = fi_area_rects(x, y, r, faceW, faceH, inv, rc);

@@ -290,6 +290,41 @@ class FrameGrid:
         return n, match
 
 
+    def fuse_search(self, dKF, Tcw, scale_factors, inv_level_sigma2, valid, Xw, level, dMP, th):
+        """The search of ORBMatcher::Fuse(pKF, vpMapPoints, th) (reference src/ORBMatcher.cpp:1126-1240); self = the KeyFrame's grid.
+        Returns (bestIdx, bestDist) per MapPoint: the key point it would be fused with (-1 / 256: none)."""
+        dKF = _u8(dKF); Tcw = _f32(Tcw).reshape(16); sf = _f32(scale_factors); isg = _f32(inv_level_sigma2); valid = _u8(valid); Xw = _f32(Xw); level = _i32(level); dMP = _u8(dMP)
+        n = len(valid); bi = np.empty(n, np.int32); bd = np.empty(n, np.int32)
+        lib().orc_fuse_search(self._h, _p(dKF), _p(Tcw), _p(sf), _p(isg), n, _p(valid), _p(Xw), _p(level), _p(dMP), C.c_float(th), _p(bi), _p(bd))
+        return bi, bd
+
+
+def distinctive_descriptors(desc, offset):
+    """MapPoint::ComputeDistinctiveDescriptors (reference src/MapPoint.cpp:243-303) for a batch of MapPoints: desc = all observation descriptors,
+    offset[p]..offset[p+1] = the rows of point p (in the order the reference iterates mObservations). Returns the chosen row per point (-1: none)."""
+    desc = _u8(desc).reshape(-1, 32); offset = _i32(offset); n = len(offset) - 1
+    best = np.empty(n, np.int32)
+    lib().orc_distinctive_descriptors(_p(desc), _p(offset), n, _p(best))
+    return best
+
+
+def search_for_triangulation(k1, d1, rays1, hasMP1, node1, k2, d2, rays2, hasMP2, node2, Ow1, Tcw2, E12, scale_factors, level_sigma2, faceW, faceH, checkOri=True):
+    """ORBMatcher::SearchForTriangulation (reference src/ORBMatcher.cpp:971-1124). Returns (nmatches, match12)."""
+    k1 = np.ascontiguousarray(k1); k2 = np.ascontiguousarray(k2); d1 = _u8(d1); d2 = _u8(d2); rays1 = _f32(rays1); rays2 = _f32(rays2)
+    hasMP1 = _u8(hasMP1); hasMP2 = _u8(hasMP2); node1 = _i32(node1); node2 = _i32(node2)
+    Ow1 = _f32(Ow1); Tcw2 = _f32(Tcw2).reshape(16); E12 = _f32(E12).reshape(9); sf = _f32(scale_factors); ls2 = _f32(level_sigma2)
+    m = np.empty(len(k1), np.int32)
+    n = lib().orc_search_for_triangulation(_p(k1), _p(d1), _p(rays1), _p(hasMP1), _p(node1), len(k1), _p(k2), _p(d2), _p(rays2), _p(hasMP2), _p(node2), len(k2), _p(Ow1), _p(Tcw2),
+                                           _p(E12), _p(sf), _p(ls2), int(faceW), int(faceH), int(checkOri), _p(m))
+    return n, m
+
+
+def vector_sigma(kx, ky, normal_rig, faceW, faceH):
+    lib().orc_vector_sigma.restype = C.c_float
+    nr = _f32(normal_rig)
+    return float(lib().orc_vector_sigma(C.c_float(kx), C.c_float(ky), _p(nr), int(faceW), int(faceH)))
+
+
 def area_rects(x, y, r, faceW, faceH):
     out = np.zeros((3, 5), np.int32)
     n = lib().orc_area_rects(C.c_float(x), C.c_float(y), C.c_float(r), int(faceW), int(faceH), _p(out))

@@ -119,6 +119,38 @@ class Ref:
                                           _p(kps), _p(desc), _p(n))
         return kps, desc, n
 
+    # ---- LocalMapping feature operations (src/MapPoint.cpp:243-303, src/ORBMatcher.cpp:971-1240) on reference KeyFrame / MapPoint objects
+    def distinctive_descriptor(self, desc):
+        desc = _u8(desc).reshape(-1, 32); out = np.zeros(32, np.uint8)
+        self.L.ref_set_camera(C.byref(self.cp))
+        self.L.ref_distinctive_descriptor(len(desc), _p(desc), _p(out))
+        return out
+
+    def fuse(self, kKF, dKF, Tcw, Xw, kObs, dMP, TcwObs, th=3.0):
+        """Returns nFused, valid, level (the pre-tests / PredictScale of Fuse, from the reference's own getters), idxInKF per MapPoint."""
+        kKF = np.ascontiguousarray(kKF); kObs = np.ascontiguousarray(kObs); Xw = _f32(Xw); n = len(Xw)
+        a = [_u8(dKF), _f32(Tcw).reshape(16), _u8(dMP), _f32(TcwObs).reshape(16)]
+        valid = np.zeros(n, np.uint8); level = np.zeros(n, np.int32); idx = np.zeros(n, np.int32)
+        self.L.ref_set_camera(C.byref(self.cp))
+        nf = self.L.ref_fuse(len(kKF), _p(kKF), _p(a[0]), _p(a[1]), n, _p(Xw), _p(kObs), _p(a[2]), _p(a[3]), C.c_float(th), _p(valid), _p(level), _p(idx))
+        return nf, valid, level, idx
+
+    def search_for_triangulation(self, k1, d1, Tcw1, hasMP1, node1, k2, d2, Tcw2, hasMP2, node2, E12, checkOri=False):
+        k1 = np.ascontiguousarray(k1); k2 = np.ascontiguousarray(k2)
+        a = [_u8(d1), _f32(Tcw1).reshape(16), _u8(hasMP1), np.ascontiguousarray(node1, np.int32), _u8(d2), _f32(Tcw2).reshape(16), _u8(hasMP2), np.ascontiguousarray(node2, np.int32),
+             _f32(E12).reshape(9)]
+        Ow1 = np.zeros(3, np.float32); m = np.empty(len(k1), np.int32)
+        self.L.ref_set_camera(C.byref(self.cp))
+        n = self.L.ref_search_for_triangulation(len(k1), _p(k1), _p(a[0]), _p(a[1]), _p(a[2]), _p(a[3]), len(k2), _p(k2), _p(a[4]), _p(a[5]), _p(a[6]), _p(a[7]), _p(a[8]),
+                                                int(checkOri), _p(Ow1), _p(m))
+        return n, m, Ow1
+
+    def vector_sigma(self, kx, ky, normal_rig):
+        self.L.ref_vector_sigma.restype = C.c_float
+        nr = _f32(normal_rig)
+        self.L.ref_set_camera(C.byref(self.cp))
+        return float(self.L.ref_vector_sigma(C.c_float(kx), C.c_float(ky), _p(nr)))
+
     def descriptor_distance(self, a, b):
         a = _u8(a); b = _u8(b)
         return self.L.ref_descriptor_distance(_p(a), _p(b))

@@ -394,3 +394,113 @@ int ref_descriptor_distance(const uint8_t* a, const uint8_t* b) {
 }
 
 }  // extern "C"
+
+// =========================================================================================== LocalMapping feature operations
+namespace {
+// KeyFrames at ascending addresses, so that std::map<KeyFrame*, size_t> iterates them in creation order (MapPoint::mObservations is keyed by pointer)
+struct KFArray {
+    char* buf; std::vector<KeyFrame*> kf;
+    KFArray(int n) : buf((char*)std::malloc((size_t)n * sizeof(KeyFrame) + 64)), kf(n, static_cast<KeyFrame*>(NULL)) {}
+    KeyFrame* make(int i, Frame& F, Map* map) { kf[i] = new (buf + (size_t)i * sizeof(KeyFrame)) KeyFrame(F, map, NULL); return kf[i]; }
+    ~KFArray() { for (KeyFrame* k : kf) if (k) k->~KeyFrame(); std::free(buf); }
+};
+}  // namespace
+
+extern "C" {
+
+// MapPoint::ComputeDistinctiveDescriptors on a MapPoint observed once in each of N key frames (observation i carries desc row i); out = mDescriptor
+void ref_distinctive_descriptor(int N, const uint8_t* desc, uint8_t* out32) {
+    Map map;
+    const float I4[16] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1};
+    const float P0[3] = {0, 0, 1};
+    KFArray A(N);
+    const KpPOD kp = {700, 700, 31, 0, 0, 0, -1};
+    for (int i = 0; i < N; i++) { Frame* F = make_frame(1, &kp, desc + 32 * (size_t)i, I4, 8, 1.2f); A.make(i, *F, &map); delete F; }
+    MapPoint* mp = new MapPoint(mat_from(P0, 3, 1), A.kf[0], &map);
+    for (int i = 0; i < N; i++) mp->AddObservation(A.kf[i], 0);
+    mp->ComputeDistinctiveDescriptors();
+    const cv::Mat d = mp->GetDescriptor();
+    std::memcpy(out32, d.ptr<uchar>(0), 32);
+    delete mp;
+}
+
+// ORBMatcher(0.6).Fuse(pKF, vpMapPoints, th) on a key frame without MapPoints. MapPoint m: position Xw, observed once, by key point m of a second
+// key frame (pose TcwObs, key points kObs - their octave fixes the scale-invariance distances - and descriptors dMP) -> UpdateNormalAndDepth +
+// ComputeDistinctiveDescriptors give it normal, distances and descriptor the way LocalMapping does. Outputs: valid / level = the pre-tests and
+// PredictScale of Fuse evaluated with the reference's own getters; idxInKF[m] = key point of pKF the MapPoint (or what replaced it) sits on after
+// the call, -1 none. Returns nFused.
+int ref_fuse(int nKF, const KpPOD* kKF, const uint8_t* dKF, const float* Tcw, int nMP, const float* Xw, const KpPOD* kObs, const uint8_t* dMP, const float* TcwObs, float th,
+             uint8_t* valid, int32_t* level, int32_t* idxInKF) {
+    Map map;
+    Frame* F = make_frame(nKF, kKF, dKF, Tcw, 8, 1.2f);
+    Frame* Fo = make_frame(nMP, kObs, dMP, TcwObs, 8, 1.2f);
+    KFArray A(2);
+    KeyFrame* pKF = A.make(0, *F, &map); KeyFrame* pObs = A.make(1, *Fo, &map);
+    delete F; delete Fo;
+    std::vector<MapPoint*> mps(nMP);
+    for (int m = 0; m < nMP; m++) {
+        MapPoint* mp = new MapPoint(mat_from(Xw + 3 * m, 3, 1), pObs, &map);
+        mp->AddObservation(pObs, m); pObs->AddMapPoint(mp, m);
+        mp->ComputeDistinctiveDescriptors(); mp->UpdateNormalAndDepth();
+        mps[m] = mp;
+    }
+    cv::Mat Ow = pKF->GetCameraCenter();
+    for (int m = 0; m < nMP; m++) {   // src/ORBMatcher.cpp:1145-1178 with the reference's own accessors
+        MapPoint* pMP = mps[m];
+        valid[m] = 0; level[m] = 0;
+        cv::Mat p3Dw = pMP->GetWorldPos();
+        const float maxDistance = pMP->GetMaxDistanceInvariance();
+        const float minDistance = pMP->GetMinDistanceInvariance();
+        cv::Mat PO = p3Dw - Ow;
+        const float dist3D = cv::norm(PO);
+        if (dist3D < minDistance || dist3D > maxDistance) continue;
+        cv::Mat Pn = pMP->GetNormal();
+        if (PO.dot(Pn) < 0.5 * dist3D) continue;
+        valid[m] = 1; level[m] = pMP->PredictScale(dist3D, pKF);
+    }
+    ORBMatcher matcher(0.6f, true);
+    const int nFused = matcher.Fuse(pKF, mps, th);
+    for (int m = 0; m < nMP; m++) {
+        MapPoint* q = mps[m];
+        while (q->GetReplaced()) q = q->GetReplaced();
+        idxInKF[m] = q->GetIndexInKeyFrame(pKF);
+    }
+    for (MapPoint* mp : mps) delete mp;
+    return nFused;
+}
+
+// ORBMatcher(0.6, checkOri).SearchForTriangulation(pKF1, pKF2, E12, pairs). node1 / node2: vocabulary node of every feature (mFeatVec), hasMP: the key
+// point already has a MapPoint. Ow1out = pKF1->GetCameraCenter(). match12[i1] = i2 or -1. Returns nmatches.
+int ref_search_for_triangulation(int n1, const KpPOD* k1, const uint8_t* d1, const float* Tcw1, const uint8_t* hasMP1, const int32_t* node1, int n2, const KpPOD* k2,
+                                 const uint8_t* d2, const float* Tcw2, const uint8_t* hasMP2, const int32_t* node2, const float* E12, int checkOri, float* Ow1out,
+                                 int32_t* match12) {
+    Map map;
+    Frame* F1 = make_frame(n1, k1, d1, Tcw1, 8, 1.2f);
+    Frame* F2 = make_frame(n2, k2, d2, Tcw2, 8, 1.2f);
+    KFArray A(2);
+    KeyFrame* kf1 = A.make(0, *F1, &map); KeyFrame* kf2 = A.make(1, *F2, &map);
+    delete F1; delete F2;
+    for (int i = 0; i < n1; i++) kf1->mFeatVec.addFeature(node1[i], i);
+    for (int i = 0; i < n2; i++) kf2->mFeatVec.addFeature(node2[i], i);
+    const float P0[3] = {0, 0, 1};
+    std::vector<MapPoint*> owned;
+    for (int i = 0; i < n1; i++) if (hasMP1[i]) { MapPoint* mp = new MapPoint(mat_from(P0, 3, 1), kf1, &map); kf1->AddMapPoint(mp, i); owned.push_back(mp); }
+    for (int i = 0; i < n2; i++) if (hasMP2[i]) { MapPoint* mp = new MapPoint(mat_from(P0, 3, 1), kf2, &map); kf2->AddMapPoint(mp, i); owned.push_back(mp); }
+    cv::Mat Ow = kf1->GetCameraCenter();
+    for (int i = 0; i < 3; i++) Ow1out[i] = Ow.at<float>(i);
+    ORBMatcher matcher(0.6f, checkOri != 0);
+    std::vector<std::pair<size_t, size_t> > pairs;
+    const int n = matcher.SearchForTriangulation(kf1, kf2, mat_from(E12, 3, 3), pairs);
+    for (int i = 0; i < n1; i++) match12[i] = -1;
+    for (size_t i = 0; i < pairs.size(); i++) match12[pairs[i].first] = (int32_t)pairs[i].second;
+    for (MapPoint* mp : owned) delete mp;
+    return n;
+}
+
+// CamModelGeneral::GetVectorSigma(key, normalRig)
+float ref_vector_sigma(float kx, float ky, const float* normalRig) {
+    cv::KeyPoint kp; kp.pt.x = kx; kp.pt.y = ky;
+    return CamModelGeneral::GetCamera()->GetVectorSigma(kp, cv::Vec3f(normalRig[0], normalRig[1], normalRig[2]));
+}
+
+}  // extern "C"
