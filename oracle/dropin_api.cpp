@@ -37,6 +37,9 @@ std::vector<cv::Mat> Converter::toDescriptorVector(const cv::Mat& Descriptors) {
 int cslam_cpu_SearchByBoW(ORBMatcher* m, KeyFrame* pKF, Frame& F, std::vector<MapPoint*>& vpMapPointMatches);
 int cslam_cpu_SearchByProjection(ORBMatcher* m, Frame& CurrentFrame, const Frame& LastFrame, const float th, const bool bMono);
 int cslam_cpu_SearchByProjection(ORBMatcher* m, Frame& F, const std::vector<MapPoint*>& vpMapPoints, const float th);
+int cslam_cpu_Fuse(ORBMatcher* m, KeyFrame* pKF, const std::vector<MapPoint*>& vpMapPoints, const float th);
+int cslam_cpu_SearchForTriangulation(ORBMatcher* m, KeyFrame* pKF1, KeyFrame* pKF2, cv::Mat E12, std::vector<std::pair<size_t, size_t> >& vMatchedPairs);
+namespace cubemap_b200 { void DistinctiveDescriptors(const std::vector<MapPoint*>& vpMPs, std::vector<cv::Mat>& out); }
 
 struct RefCam { double c, d, e, u0, v0, p[5], invp[12]; int Iw, Ih, faceW, faceH; double fov; };
 
@@ -221,6 +224,98 @@ int dropin_local_ba(int nKF, int nMP, int nE, float* Tcw, float* pts, const int3
     for (int l = 0; l < nMP; l++) { const cv::Mat P = mps[l]->GetWorldPos(); for (int c = 0; c < 3; c++) pts[3 * l + c] = P.at<float>(c); }
     for (int e = 0; e < nE; e++) erased[e] = mps[eMP[e]]->IsInKeyFrame(kfs[eKF[e]]) ? 0 : 1;
     return window;   // (objects are intentionally leaked: the reference's Map owns raw pointers and has no teardown, include/System.h:93-95)
+}
+
+
+// ORBMatcher(0.6).Fuse(pKF, vpMapPoints, th) (LocalMapping::SearchInNeighbors): the GPU drop-in and the reference's own CPU body on identical object
+// graphs (a key frame without MapPoints; MapPoint m observed once, by key point m of a second key frame). idx*[m] = key point of pKF on which the
+// MapPoint (or what replaced it) sits afterwards, -1 none; bad*[m] = isBad(). nFused by return values.
+void dropin_fuse(int nKF, const KpPOD* kKF, const uint8_t* dKF, const float* Tcw, int nMP, const float* Xw, const KpPOD* kObs, const uint8_t* dMP, const float* TcwObs, float th,
+                 int32_t* idxGpu, uint8_t* badGpu, int32_t* nGpu, int32_t* idxCpu, uint8_t* badCpu, int32_t* nCpu) {
+    for (int pass = 0; pass < 2; pass++) {
+        Map* map = new Map();
+        Frame* F = make_frame(nKF, kKF, dKF, Tcw, 8, 1.2f); build_grid(F);
+        Frame* Fo = make_frame(nMP, kObs, dMP, TcwObs, 8, 1.2f); build_grid(Fo);
+        KeyFrame* pKF = new KeyFrame(*F, map, NULL); KeyFrame* pObs = new KeyFrame(*Fo, map, NULL);
+        delete F; delete Fo;
+        std::vector<MapPoint*> mps(nMP);
+        for (int m = 0; m < nMP; m++) {
+            MapPoint* mp = new MapPoint(mat_from(Xw + 3 * m, 3, 1), pObs, map);
+            mp->AddObservation(pObs, m); pObs->AddMapPoint(mp, m);
+            mp->ComputeDistinctiveDescriptors(); mp->UpdateNormalAndDepth();
+            mps[m] = mp;
+        }
+        ORBMatcher matcher(0.6f, true);
+        const int n = pass == 0 ? matcher.Fuse(pKF, mps, th)                 // dropin/ORBMatcher_mapping_b200.cpp -> libcubemap_b200.so
+                                : cslam_cpu_Fuse(&matcher, pKF, mps, th);    // src/ORBMatcher.cpp:1126-1240
+        (pass == 0 ? *nGpu : *nCpu) = n;
+        int32_t* idx = pass == 0 ? idxGpu : idxCpu; uint8_t* bad = pass == 0 ? badGpu : badCpu;
+        for (int m = 0; m < nMP; m++) {
+            MapPoint* q = mps[m];
+            bad[m] = q->isBad();
+            while (q->GetReplaced()) q = q->GetReplaced();
+            idx[m] = q->GetIndexInKeyFrame(pKF);
+        }
+        // (objects are intentionally leaked: the reference's Map owns raw pointers and has no teardown)
+    }
+}
+
+// ORBMatcher(0.6, checkOri).SearchForTriangulation(pKF1, pKF2, E12, pairs) (LocalMapping::CreateNewMapPoints): GPU drop-in vs the reference's CPU body
+void dropin_search_for_triangulation(int n1, const KpPOD* k1, const uint8_t* d1, const float* Tcw1, const uint8_t* hasMP1, const int32_t* node1, int n2, const KpPOD* k2,
+                                     const uint8_t* d2, const float* Tcw2, const uint8_t* hasMP2, const int32_t* node2, const float* E12, int checkOri, int32_t* matchGpu,
+                                     int32_t* nGpu, int32_t* matchCpu, int32_t* nCpu) {
+    Map* map = new Map();
+    Frame* F1 = make_frame(n1, k1, d1, Tcw1, 8, 1.2f); build_grid(F1);
+    Frame* F2 = make_frame(n2, k2, d2, Tcw2, 8, 1.2f); build_grid(F2);
+    KeyFrame* kf1 = new KeyFrame(*F1, map, NULL); KeyFrame* kf2 = new KeyFrame(*F2, map, NULL);
+    delete F1; delete F2;
+    for (int i = 0; i < n1; i++) kf1->mFeatVec.addFeature(node1[i], i);
+    for (int i = 0; i < n2; i++) kf2->mFeatVec.addFeature(node2[i], i);
+    const float P0[3] = {0, 0, 1};
+    for (int i = 0; i < n1; i++) if (hasMP1[i]) kf1->AddMapPoint(new MapPoint(mat_from(P0, 3, 1), kf1, map), i);
+    for (int i = 0; i < n2; i++) if (hasMP2[i]) kf2->AddMapPoint(new MapPoint(mat_from(P0, 3, 1), kf2, map), i);
+    for (int pass = 0; pass < 2; pass++) {
+        ORBMatcher matcher(0.6f, checkOri != 0);
+        std::vector<std::pair<size_t, size_t> > pairs;
+        const int n = pass == 0 ? matcher.SearchForTriangulation(kf1, kf2, mat_from(E12, 3, 3), pairs)                  // dropin/ORBMatcher_mapping_b200.cpp
+                                : cslam_cpu_SearchForTriangulation(&matcher, kf1, kf2, mat_from(E12, 3, 3), pairs);    // src/ORBMatcher.cpp:971-1124
+        (pass == 0 ? *nGpu : *nCpu) = n;
+        int32_t* out = pass == 0 ? matchGpu : matchCpu;
+        for (int i = 0; i < n1; i++) out[i] = -1;
+        for (size_t i = 0; i < pairs.size(); i++) out[pairs[i].first] = (int32_t)pairs[i].second;
+    }
+}
+
+// cubemap_b200::DistinctiveDescriptors (the batched form of MapPoint::ComputeDistinctiveDescriptors) vs the member itself, on MapPoints observed
+// in `nobs[p]` key frames each (descriptor rows back to back). equal[p] = the batched descriptor is byte-identical to mDescriptor after the member ran.
+void dropin_distinctive_batch(int nPoints, const int32_t* offset, const uint8_t* desc, uint8_t* equal) {
+    Map* map = new Map();
+    const float I4[16] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1};
+    const float P0[3] = {0, 0, 1};
+    int maxObs = 0;
+    for (int p = 0; p < nPoints; p++) maxObs = std::max(maxObs, offset[p + 1] - offset[p]);
+    // key frame j lends row p of its descriptors to MapPoint p (rows of points with fewer observations stay unused)
+    std::vector<KeyFrame*> kfs(maxObs);
+    for (int j = 0; j < maxObs; j++) {
+        std::vector<KpPOD> kps(nPoints, KpPOD{700, 700, 31, 0, 0, 0, -1}); std::vector<uint8_t> d((size_t)nPoints * 32, 0);
+        for (int p = 0; p < nPoints; p++) if (offset[p] + j < offset[p + 1]) std::memcpy(&d[(size_t)p * 32], desc + 32 * (size_t)(offset[p] + j), 32);
+        Frame* F = make_frame(nPoints, kps.data(), d.data(), I4, 8, 1.2f);
+        kfs[j] = new KeyFrame(*F, map, NULL);
+        delete F;
+    }
+    std::vector<MapPoint*> mps(nPoints);
+    for (int p = 0; p < nPoints; p++) {
+        mps[p] = new MapPoint(mat_from(P0, 3, 1), kfs.empty() ? static_cast<KeyFrame*>(NULL) : kfs[0], map);
+        for (int j = 0; offset[p] + j < offset[p + 1]; j++) mps[p]->AddObservation(kfs[j], p);
+    }
+    std::vector<cv::Mat> batched;
+    cubemap_b200::DistinctiveDescriptors(mps, batched);                        // dropin/MapPoint_batch_b200.cpp -> libcubemap_b200.so
+    for (int p = 0; p < nPoints; p++) {
+        mps[p]->ComputeDistinctiveDescriptors();                               // src/MapPoint.cpp:243-303
+        const cv::Mat d = mps[p]->GetDescriptor();
+        if (offset[p + 1] == offset[p]) equal[p] = batched[p].empty();
+        else equal[p] = !batched[p].empty() && std::memcmp(batched[p].ptr<uchar>(0), d.ptr<uchar>(0), 32) == 0;
+    }
 }
 
 }  // extern "C"

@@ -144,3 +144,61 @@ def test_search_by_projection_on_reference_frames(oracle, seed, th):
     assert np.array_equal(mg, mc)
     # fixture switches the singleton camera back for the other tests of this module
     L.dropin_set_camera(C.byref(oracle.cam_params(config.lafida_450())))
+
+
+def _front(oracle):
+    if not os.path.exists(LIB):
+        pytest.skip("oracle/_ref/libdropin.so is built in the build container")
+    L = C.CDLL(LIB)
+    L.dropin_set_camera(C.byref(oracle.cam_params(config.front_1024())))
+    return L
+
+
+@pytest.mark.parametrize("seed,th", [(0, 3.0), (1, 6.0)])
+def test_fuse_on_reference_key_frames(oracle, seed, th):
+    """ORBMatcher(0.6).Fuse(pKF, vpMapPoints, th) (src/LocalMapping.cpp:402,423) on reference KeyFrame / MapPoint objects: the GPU drop-in (search on
+    the device, Replace / AddObservation bookkeeping through the reference's own methods) and the reference's CPU body leave identical maps."""
+    L = _front(oracle)
+    s = synth.mapping_pair(seed, n=1500, faceW=650)
+    n = len(s["Xw"])
+    a = [np.ascontiguousarray(s["kCur"]), np.ascontiguousarray(s["dCur"]), np.ascontiguousarray(s["TcwCur"], np.float32), np.ascontiguousarray(s["Xw"], np.float32),
+         np.ascontiguousarray(s["kLast"]), np.ascontiguousarray(s["dLast"]), np.ascontiguousarray(s["TcwLast"], np.float32)]
+    ig = np.zeros(n, np.int32); ic = np.zeros(n, np.int32); bg = np.zeros(n, np.uint8); bc = np.zeros(n, np.uint8); ng = C.c_int32(); nc = C.c_int32()
+    L.dropin_fuse(len(a[0]), _p(a[0]), _p(a[1]), _p(a[2]), n, _p(a[3]), _p(a[4]), _p(a[5]), _p(a[6]), C.c_float(th), _p(ig), _p(bg), C.byref(ng), _p(ic), _p(bc), C.byref(nc))
+    assert ng.value == nc.value > 150
+    assert np.array_equal(ig, ic) and np.array_equal(bg, bc)
+    L.dropin_set_camera(C.byref(oracle.cam_params(config.lafida_450())))
+
+
+@pytest.mark.parametrize("seed,ori", [(0, False), (1, True)])
+def test_search_for_triangulation_on_reference_key_frames(oracle, seed, ori):
+    """ORBMatcher(0.6, false).SearchForTriangulation(pKF1, pKF2, E12, pairs) (src/LocalMapping.cpp:262): drop-in == the reference's CPU body."""
+    L = _front(oracle)
+    s = synth.mapping_pair(30 + seed, n=1500, faceW=650)
+    n1, n2 = len(s["kCur"]), len(s["kLast"])
+    a = [np.ascontiguousarray(s["kCur"]), np.ascontiguousarray(s["dCur"]), np.ascontiguousarray(s["TcwCur"], np.float32), np.ascontiguousarray(s["hasMPCur"]),
+         np.ascontiguousarray(s["nodeCur"], np.int32), np.ascontiguousarray(s["kLast"]), np.ascontiguousarray(s["dLast"]), np.ascontiguousarray(s["TcwLast"], np.float32),
+         np.ascontiguousarray(s["hasMPObs"]), np.ascontiguousarray(s["nodeObs"], np.int32), np.ascontiguousarray(s["E12"], np.float32)]
+    mg = np.zeros(n1, np.int32); mc = np.zeros(n1, np.int32); ng = C.c_int32(); nc = C.c_int32()
+    L.dropin_search_for_triangulation(n1, _p(a[0]), _p(a[1]), _p(a[2]), _p(a[3]), _p(a[4]), n2, _p(a[5]), _p(a[6]), _p(a[7]), _p(a[8]), _p(a[9]), _p(a[10]), int(ori), _p(mg),
+                                      C.byref(ng), _p(mc), C.byref(nc))
+    assert ng.value == nc.value > 100
+    assert np.array_equal(mg, mc)
+    L.dropin_set_camera(C.byref(oracle.cam_params(config.lafida_450())))
+
+
+def test_batched_distinctive_descriptors_on_reference_map_points(oracle):
+    """cubemap_b200::DistinctiveDescriptors (one launch for all MapPoints of a key frame) == MapPoint::ComputeDistinctiveDescriptors per point."""
+    L = _front(oracle)
+    rng = np.random.default_rng(3)
+    P = 400; off = [0]; rows = []
+    for p in range(P):
+        N = int(rng.choice([0, 1, 2, 3, 5, 8, 12]))
+        base = rng.integers(0, 256, 32, dtype=np.uint8)
+        for _ in range(N):
+            rows.append(base ^ np.packbits(rng.random(256) < rng.uniform(0.0, 0.25), bitorder="little"))
+        off.append(off[-1] + N)
+    desc = np.ascontiguousarray(np.stack(rows)); off = np.array(off, np.int32); eq = np.zeros(P, np.uint8)
+    L.dropin_distinctive_batch(P, _p(off), _p(desc), _p(eq))
+    assert eq.all()
+    L.dropin_set_camera(C.byref(oracle.cam_params(config.lafida_450())))
