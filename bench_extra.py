@@ -4,6 +4,7 @@ sample, core count stated) and an end-to-end figure through the host entry point
   local_ba           configs[3]: LocalBundleAdjustment 50 KF x 20k MapPoints (the "LocalBA iters/sec" half of the metric) + the dense k=50 variant
   pose_optimization  PoseOptimization batches
   tracking           configs[4]: warp -> extract -> frame index -> SearchByProjection(last frame) -> pose-only BA, device-resident per frame batch
+  local_mapping      SURVEY §8(f) rank 4: batched ComputeDistinctiveDescriptors, Fuse search, SearchForTriangulation (host calls)
 Multi-GPU (run_multi): landmark-sharded LocalBA with parity against the 1-GPU run, pair-sharded matching, frame-sharded tracking."""
 import json
 import os
@@ -265,12 +266,83 @@ def _tracking_leg(torch, dev, args, local, rank=0, world=1):
     return out
 
 
+def _mapping_leg(args, local):
+    """LocalMapping feature operations through the host calls (the only form they have): batched ComputeDistinctiveDescriptors, Fuse search,
+    SearchForTriangulation over 20 key-frame pairs; oracle on the same inputs as the CPU baseline (one thread: the mapping thread)."""
+    from cubemapslam_b200.mapper import Mapper
+    import oracle as orc
+    m = Mapper(device=local)
+    rng = np.random.default_rng(5)
+    out = {}
+    # ---- distinctive descriptors: 20 000 MapPoints x 3..15 observations
+    P = 20000
+    nobs = rng.integers(3, 16, P); off = np.concatenate([[0], np.cumsum(nobs)]).astype(np.int32)
+    base = rng.integers(0, 256, (P, 32), dtype=np.uint8)
+    desc = np.repeat(base, nobs, axis=0) ^ np.packbits(rng.random((int(off[-1]), 256)) < 0.08, axis=1, bitorder="little")
+    m.ComputeDistinctiveDescriptors(desc[:off[100]], off[:101])
+    t0 = time.perf_counter(); g = m.ComputeDistinctiveDescriptors(desc, off); dt = time.perf_counter() - t0
+    sub = 2000
+    t0 = time.perf_counter(); r = orc.distinctive_descriptors(desc[:off[sub]], off[:sub + 1]); dtc = time.perf_counter() - t0
+    out["distinctive_descriptors"] = {"config": "%d MapPoints, %d observation descriptors, one host call" % (P, int(off[-1])), "points_per_s": round(P / dt, 1), "seconds": round(dt, 5),
+                                      "e2e": {"points_per_s": round(P / dt, 1), "h2d_bytes": int(off[-1]) * 32 + 4 * (P + 1), "d2h_bytes": 4 * P},
+                                      "roofline": {"bound": "latency / PCIe of one small call (9 N^2 Hamming per point; %.1f MB in)" % (int(off[-1]) * 32 / 1e6)},
+                                      "cpu_baseline": {"points_per_s": round(sub / dtc, 1), "cores": 1, "kind": "port", "sample": "%d points, one thread" % sub},
+                                      "equal_to_oracle": bool(np.array_equal(g[:sub], r))}
+    # ---- Fuse search + SearchForTriangulation on synthetic key-frame pairs
+    ss = [synth.mapping_pair(40 + i, n=2000, faceW=650) for i in range(4)]
+    s = ss[0]; n = len(s["Xw"])
+    valid = np.ones(n, np.uint8); level = np.clip(s["kLast"]["octave"], 0, 7).astype(np.int32)
+    m.FuseSearch(s["kCur"], s["dCur"], s["TcwCur"], valid, s["Xw"], level, s["dLast"], 3.0, s["scale"], s["inv_level_sigma2"], 650, 650)
+    reps = 20
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        gi, gd = m.FuseSearch(s["kCur"], s["dCur"], s["TcwCur"], valid, s["Xw"], level, s["dLast"], 3.0, s["scale"], s["inv_level_sigma2"], 650, 650)
+    dt = (time.perf_counter() - t0) / reps
+    grid = orc.FrameGrid(s["kCur"], 650, 650)
+    t0 = time.perf_counter(); bi, bd = grid.fuse_search(s["dCur"], s["TcwCur"], s["scale"], s["inv_level_sigma2"], valid, s["Xw"], level, s["dLast"], 3.0); dtc = time.perf_counter() - t0
+    out["fuse_search"] = {"config": "Fuse(pKF, %d MapPoints, th 3) against a key frame of %d key points, one host call" % (n, len(s["kCur"])), "calls_per_s": round(1 / dt, 1),
+                          "map_points_per_s": round(n / dt, 1), "e2e": {"calls_per_s": round(1 / dt, 1), "note": "host arrays in / out, frame index built inside the call"},
+                          "roofline": {"bound": "latency (3 launches + 9 small copies per call)"},
+                          "cpu_baseline": {"calls_per_s": round(1 / dtc, 1), "cores": 1, "kind": "port", "sample": "the same call, one thread (grid prebuilt)"},
+                          "equal_to_oracle": bool(np.array_equal(gi, bi) and np.array_equal(gd, bd))}
+    P2 = 20
+    s1 = max(len(q["kCur"]) for q in ss); s2 = max(len(q["kLast"]) for q in ss)
+    KP = ss[0]["kCur"].dtype
+    k1 = np.zeros((P2, s1), KP); d1 = np.zeros((P2, s1, 32), np.uint8); r1 = np.zeros((P2, s1, 3), np.float32); h1 = np.zeros((P2, s1), np.uint8); nd1 = np.zeros((P2, s1), np.int32)
+    k2 = np.zeros((P2, s2), KP); d2 = np.zeros((P2, s2, 32), np.uint8); r2 = np.zeros((P2, s2, 3), np.float32); h2 = np.zeros((P2, s2), np.uint8); nd2 = np.zeros((P2, s2), np.int32)
+    n1 = np.zeros(P2, np.int32); n2 = np.zeros(P2, np.int32); Ow = np.zeros((P2, 3), np.float32); T2 = np.zeros((P2, 16), np.float32); E = np.zeros((P2, 9), np.float32)
+    rays = [(orc.key_point_rays(q["kCur"], 650, 650)[0], orc.key_point_rays(q["kLast"], 650, 650)[0]) for q in ss]
+    for p in range(P2):
+        q = ss[p % len(ss)]; ra, rb = rays[p % len(ss)]
+        a, b = len(q["kCur"]), len(q["kLast"]); n1[p] = a; n2[p] = b
+        k1[p, :a] = q["kCur"]; d1[p, :a] = q["dCur"]; r1[p, :a] = ra; h1[p, :a] = q["hasMPCur"]; nd1[p, :a] = q["nodeCur"]
+        k2[p, :b] = q["kLast"]; d2[p, :b] = q["dLast"]; r2[p, :b] = rb; h2[p, :b] = q["hasMPObs"]; nd2[p, :b] = q["nodeObs"]
+        T1 = q["TcwCur"].astype(np.float64)
+        Ow[p] = (-T1[:3, :3].T @ T1[:3, 3]).astype(np.float32); T2[p] = q["TcwLast"].reshape(16); E[p] = q["E12"].reshape(9)
+    m.SearchForTriangulation(k1[:2], d1[:2], r1[:2], h1[:2], nd1[:2], n1[:2], k2[:2], d2[:2], r2[:2], h2[:2], nd2[:2], n2[:2], Ow[:2], T2[:2], E[:2], s["scale"], s["level_sigma2"], 650, 650)
+    t0 = time.perf_counter()
+    nm, mm = m.SearchForTriangulation(k1, d1, r1, h1, nd1, n1, k2, d2, r2, h2, nd2, n2, Ow, T2, E, s["scale"], s["level_sigma2"], 650, 650)
+    dt = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    w = [orc.search_for_triangulation(ss[p]["kCur"], ss[p]["dCur"], rays[p][0], ss[p]["hasMPCur"], ss[p]["nodeCur"], ss[p]["kLast"], ss[p]["dLast"], rays[p][1], ss[p]["hasMPObs"],
+                                      ss[p]["nodeObs"], Ow[p], T2[p], E[p], s["scale"], s["level_sigma2"], 650, 650, False) for p in range(len(ss))]
+    dtc = time.perf_counter() - t0
+    out["search_for_triangulation"] = {"config": "%d key-frame pairs x ~%d features per key frame, one host call (LocalMapping::CreateNewMapPoints matches ~20 neighbours)" % (P2, s1),
+                                       "pairs_per_s": round(P2 / dt, 1), "e2e": {"pairs_per_s": round(P2 / dt, 1), "note": "host arrays in / out"},
+                                       "mean_matches": round(float(nm.mean()), 1), "roofline": {"bound": "latency (one CTA per pair: in-CTA sort + node scans)"},
+                                       "cpu_baseline": {"pairs_per_s": round(len(ss) / dtc, 1), "cores": 1, "kind": "port", "sample": "%d pairs, one thread" % len(ss)},
+                                       "equal_to_oracle": bool(all(nm[p] == w[p][0] and np.array_equal(mm[p, :n1[p]], w[p][1]) for p in range(len(ss))))}
+    m.close()
+    return out
+
+
 def run(args, local):
     import torch
     dev = torch.device("cuda", local)
     out = {}
     for name, fn in (("match", lambda: _match_leg(torch, dev, args, local)), ("local_ba", lambda: _ba_leg(args, local)), ("local_ba_dense", lambda: _ba_leg(args, local, dense=True)),
-                     ("pose_optimization", lambda: _pose_leg(args, local)), ("tracking", lambda: _tracking_leg(torch, dev, args, local))):
+                     ("pose_optimization", lambda: _pose_leg(args, local)), ("tracking", lambda: _tracking_leg(torch, dev, args, local)),
+                     ("local_mapping", lambda: _mapping_leg(args, local))):
         try:
             out[name] = fn()
         except Exception as e:  # the headline metric must still be reported

@@ -11,7 +11,7 @@ ap.add_argument("--match-steps", type=int, default=1)
 ap.add_argument("--pose-frames", type=int, default=512)
 ap.add_argument("--track-frames", type=int, default=128)
 ap.add_argument("--batch", type=int, default=128)
-ap.add_argument("--legs", default="match,pose,tracking")
+ap.add_argument("--legs", default="match,pose,tracking,mapping")
 args = ap.parse_args()
 torch.cuda.set_device(0)
 dev = torch.device("cuda", 0)
@@ -23,4 +23,6 @@ if "pose" in legs:
     out["pose_optimization"] = bench_extra._pose_leg(args, 0)
 if "tracking" in legs:
     out["tracking"] = bench_extra._tracking_leg(torch, dev, args, 0)
+if "mapping" in legs:
+    out["local_mapping"] = bench_extra._mapping_leg(args, 0)
 print(json.dumps(out))
