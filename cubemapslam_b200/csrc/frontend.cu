@@ -803,6 +803,7 @@ struct cslam_frontend {
     static const int MAX_LANES = 4;
     cudaStream_t lane[MAX_LANES] = {nullptr, nullptr, nullptr, nullptr}; cudaEvent_t evLane[MAX_LANES] = {nullptr, nullptr, nullptr, nullptr}; cudaEvent_t evFork = nullptr;
     int devLanes = 2;                // lanes used by cslam_frontend_run_dev (env CSLAM_DEV_LANES)
+    int hostChunks = 8;              // chunks a host-buffer batch is cut into (env CSLAM_HOST_CHUNKS)
     int64_t launches = 0;
     int lastBatch = 0;
     // optional per-kernel timing (cslam_frontend_set_timing): events between launches, accumulated per kernel kind
@@ -938,6 +939,7 @@ extern "C" int cslam_frontend_create(cslam_frontend** out, int device, const csl
         if (cudaStreamCreateWithFlags(&fe->lane[i], cudaStreamNonBlocking) != cudaSuccess || cudaEventCreateWithFlags(&fe->evLane[i], cudaEventDisableTiming) != cudaSuccess) { set_error("lane stream creation failed"); return fail(CSLAM_E_CUDA); }
     if (cudaEventCreateWithFlags(&fe->evFork, cudaEventDisableTiming) != cudaSuccess) { set_error("event creation failed"); return fail(CSLAM_E_CUDA); }
     if (const char* e = getenv("CSLAM_DEV_LANES")) fe->devLanes = std::max(1, std::min(atoi(e), (int)cslam_frontend::MAX_LANES));
+    if (const char* e = getenv("CSLAM_HOST_CHUNKS")) fe->hostChunks = std::max(1, std::min(atoi(e), 64));
     if (cudaMemcpyToSymbol(c_umax, fe->umax, sizeof(fe->umax)) != cudaSuccess) { set_error("cudaMemcpyToSymbol failed"); return fail(CSLAM_E_CUDA); }
     // ---- level geometry (ComputePyramid :930-936, ComputeKeyPointsOctTree :747-761)
     std::memset(&fe->L, 0, sizeof(fe->L));
@@ -1226,13 +1228,16 @@ static int run_host(cslam_frontend* fe, const uint8_t* in, size_t inFrameBytes, 
     int rc;
     if ((rc = prepare_level0(fe, fromWarp))) return rc;
     const int nlanes = lanes_for(fe, batch, 4);
+    // the batch is cut into more chunks than there are streams (chunk c runs on stream c % nlanes): the first upload - the only one nothing overlaps -
+    // is then 1/8 of the batch instead of 1/4, and the copy engines stay busy behind the kernels of earlier chunks
+    const int nchunks = fe->timing ? 1 : std::max(nlanes, std::min(fe->hostChunks, std::max(1, batch / 8)));
     const bool pinIn = is_pinned(in), pinK = is_pinned(kps), pinD = is_pinned(desc), pinN = is_pinned(n_out);
     const size_t nk = (size_t)fe->kpCap;
     if ((rc = fork_lanes(fe, nlanes))) return rc;
-    for (int ln = 0; ln < nlanes; ln++) {
-        const int f0 = (int)((long long)batch * ln / nlanes), f1 = (int)((long long)batch * (ln + 1) / nlanes), cnt = f1 - f0;
+    for (int ck = 0; ck < nchunks; ck++) {
+        const int f0 = (int)((long long)batch * ck / nchunks), f1 = (int)((long long)batch * (ck + 1) / nchunks), cnt = f1 - f0;
         if (cnt <= 0) continue;
-        cudaStream_t st = fe->lane[ln];
+        cudaStream_t st = fe->lane[ck % nlanes];
         if (fromWarp) {
             const uint8_t* src = in + (size_t)f0 * inFrameBytes;
             if (!pinIn) { std::memcpy(fe->h_pin_in + (size_t)f0 * inFrameBytes, src, (size_t)cnt * inFrameBytes); src = fe->h_pin_in + (size_t)f0 * inFrameBytes; }

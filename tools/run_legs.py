@@ -23,6 +23,8 @@ if "pose" in legs:
     out["pose_optimization"] = bench_extra._pose_leg(args, 0)
 if "tracking" in legs:
     out["tracking"] = bench_extra._tracking_leg(torch, dev, args, 0)
+if "latency" in legs:
+    out["single_frame_latency"] = bench_extra._latency_leg(args, 0)
 if "mapping" in legs:
     out["local_mapping"] = bench_extra._mapping_leg(args, 0)
 print(json.dumps(out))
