@@ -56,10 +56,14 @@ struct BfLayout { int strideA, strideB, angStride; const int32_t* nAarr; const i
 __global__ void __launch_bounds__(BF_THREADS) k_match_bruteforce(const uint8_t* __restrict__ descA, const float* __restrict__ angA, int nA_,
                                                                  const uint8_t* __restrict__ descB, const float* __restrict__ angB, int nB_, float nnratio,
                                                                  int thLow, int checkOri, int32_t* __restrict__ match12, int32_t* __restrict__ dist12,
-                                                                 int32_t* __restrict__ second12, int32_t* __restrict__ nmatches, BfLayout L) {
+                                                                 int32_t* __restrict__ second12, int32_t* __restrict__ nmatches, BfLayout L, int* __restrict__ gHist) {
+    // gridDim.y > 1: the rows of A are dealt to several CTAs per pair (a batch of ~128 pairs would otherwise leave 148 SMs one CTA each, or none);
+    // the rotation histogram then goes through gHist[pair][32] (30 bins, total, arrival counter; zeroed by the launcher) and the CTA that arrives
+    // last applies the three-maxima filter to the whole pair.
     __shared__ __align__(16) uint4 sB[2 * BF_TILE];
     __shared__ int hist[HISTO_BINS], keep[HISTO_BINS], total;
-    const int pair = blockIdx.x, tid = threadIdx.x;
+    __shared__ bool lastCta;
+    const int pair = blockIdx.x, tid = threadIdx.x, part = blockIdx.y, parts = gridDim.y;
     const int nA = L.nAarr ? min(L.nAarr[pair], L.strideA) : nA_, nB = L.nBarr ? min(L.nBarr[pair], L.strideB) : nB_;
     const uint4* A4 = reinterpret_cast<const uint4*>(descA + (size_t)pair * L.strideA * 32);
     const uint4* B4 = reinterpret_cast<const uint4*>(descB + (size_t)pair * L.strideB * 32);
@@ -69,7 +73,7 @@ __global__ void __launch_bounds__(BF_THREADS) k_match_bruteforce(const uint8_t* 
     if (tid < HISTO_BINS) hist[tid] = 0;
     if (tid == 0) total = 0;
     __syncthreads();
-    for (int rbase = 0; rbase < nA; rbase += BF_THREADS) {
+    for (int rbase = part * BF_THREADS; rbase < nA; rbase += parts * BF_THREADS) {
         const int i = rbase + tid;
         uint32_t a[8] = {0, 0, 0, 0, 0, 0, 0, 0};
         if (i < nA) {
@@ -104,11 +108,25 @@ __global__ void __launch_bounds__(BF_THREADS) k_match_bruteforce(const uint8_t* 
         }
     }
     __syncthreads();
+    if (parts > 1) {
+        int* g = gHist + (size_t)pair * 32;
+        if (tid < HISTO_BINS && hist[tid]) atomicAdd(g + tid, hist[tid]);
+        if (tid == 0 && total) atomicAdd(g + 30, total);
+        __threadfence();
+        __syncthreads();
+        if (tid == 0) lastCta = atomicAdd(g + 31, 1) == parts - 1;
+        __syncthreads();
+        if (!lastCta) return;
+        __threadfence();
+        if (tid < HISTO_BINS) hist[tid] = __ldcg(g + tid);
+        if (tid == 0) total = __ldcg(g + 30);
+        __syncthreads();
+    }
     if (checkOri) {
         if (tid == 0) three_maxima(hist, keep);
         __syncthreads();
         for (int i = tid; i < nA; i += BF_THREADS) {
-            const int m = m12[i];
+            const int m = parts > 1 ? __ldcg(m12 + i) : m12[i];
             if (m >= 0 && !keep[rot_bin(aA[(size_t)i * L.angStride], aB[(size_t)m * L.angStride])]) { m12[i] = -1; atomicSub(&total, 1); }
         }
         __syncthreads();
@@ -259,6 +277,7 @@ struct cslam_matcher {
     float *aA = nullptr, *aB = nullptr;
     int32_t *nodeA = nullptr, *nodeB = nullptr, *dMatch = nullptr, *dDist = nullptr, *dSecond = nullptr, *dN = nullptr;
     cslam_keypoint* dKps = nullptr;   // staging of cslam_match_frames (lazily allocated)
+    int* dHist = nullptr;             // per-pair rotation histogram of the row-split brute-force launches (lazily allocated)
     int64_t launches = 0;
 };
 
@@ -288,7 +307,7 @@ extern "C" void cslam_matcher_destroy(cslam_matcher* m) {
     if (!m) return;
     cudaSetDevice(m->device);
     if (m->stream) { cudaStreamSynchronize(m->stream); cudaStreamDestroy(m->stream); }
-    void* ptrs[] = {m->dA, m->dB, m->dValid, m->aA, m->aB, m->nodeA, m->nodeB, m->dMatch, m->dDist, m->dSecond, m->dN, m->dKps};
+    void* ptrs[] = {m->dA, m->dB, m->dValid, m->aA, m->aB, m->nodeA, m->nodeB, m->dMatch, m->dDist, m->dSecond, m->dN, m->dKps, m->dHist};
     for (void* p : ptrs) if (p) cudaFree(p);
     delete m;
 }
@@ -299,6 +318,21 @@ extern "C" int cslam_matcher_sync(cslam_matcher* m) {
     CSLAM_CUDA(cudaSetDevice(m->device));
     CSLAM_CUDA(cudaStreamSynchronize(m->stream));
     return CSLAM_OK;
+}
+
+// CTAs per pair of a brute-force launch: enough CTAs for ~2 per SM when the batch of pairs is small; the per-pair histogram buffer is zeroed here
+static int bf_split(cslam_matcher* m, int npairs, int** gHist) {
+    int sms = 148;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, m->device);
+    int parts = 1;
+    if (npairs < 2 * sms) parts = std::min(4, (2 * sms + npairs - 1) / npairs);
+    *gHist = nullptr;
+    if (parts > 1) {
+        if (!m->dHist && cudaMalloc(&m->dHist, (size_t)2 * sms * 32 * sizeof(int)) != cudaSuccess) { cudaGetLastError(); return 1; }   // npairs < 2 * sms whenever parts > 1
+        if (cudaMemsetAsync(m->dHist, 0, (size_t)npairs * 32 * sizeof(int), m->stream) != cudaSuccess) return 1;
+        *gHist = m->dHist;
+    }
+    return parts;
 }
 
 static int check_sizes(cslam_matcher* m, int nA, int nB, int npairs) {
@@ -317,7 +351,8 @@ extern "C" int cslam_match_bruteforce_dev(cslam_matcher* m, const uint8_t* descA
     if (rc) return rc;
     if (nA == 0) { CSLAM_CUDA(cudaMemsetAsync(nmatches, 0, (size_t)npairs * 4, m->stream)); return CSLAM_OK; }
     const BfLayout L = {nA, nB, 1, nullptr, nullptr};
-    k_match_bruteforce<<<npairs, BF_THREADS, 0, m->stream>>>(descA, angA, nA, descB, angB, nB, nnratio, th_low, check_ori, match12, dist12, second12, nmatches, L);
+    int* gHist; const int parts = bf_split(m, npairs, &gHist);
+    k_match_bruteforce<<<dim3(npairs, parts), BF_THREADS, 0, m->stream>>>(descA, angA, nA, descB, angB, nB, nnratio, th_low, check_ori, match12, dist12, second12, nmatches, L, gHist);
     m->launches++;
     CSLAM_CUDA(cudaGetLastError());
     return CSLAM_OK;
@@ -350,8 +385,9 @@ extern "C" int cslam_match_frames_dev(cslam_matcher* m, const cslam_keypoint* kp
     CSLAM_CUDA(cudaSetDevice(m->device));
     const float* ang = &kps[0].angle;
     const BfLayout L = {kp_stride, kp_stride, (int)(sizeof(cslam_keypoint) / sizeof(float)), n, n + 1};
-    k_match_bruteforce<<<nframes - 1, BF_THREADS, 0, m->stream>>>(desc, ang, 0, desc + (size_t)kp_stride * 32, ang + (size_t)kp_stride * L.angStride, 0, nnratio, th_low, check_ori,
-                                                                   match12, nullptr, nullptr, nmatches, L);
+    int* gHist; const int parts = bf_split(m, nframes - 1, &gHist);
+    k_match_bruteforce<<<dim3(nframes - 1, parts), BF_THREADS, 0, m->stream>>>(desc, ang, 0, desc + (size_t)kp_stride * 32, ang + (size_t)kp_stride * L.angStride, 0, nnratio, th_low,
+                                                                                check_ori, match12, nullptr, nullptr, nmatches, L, gHist);
     m->launches++;
     CSLAM_CUDA(cudaGetLastError());
     return CSLAM_OK;
