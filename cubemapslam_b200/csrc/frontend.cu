@@ -1100,6 +1100,7 @@ extern "C" int64_t cslam_frontend_launches(const cslam_frontend* fe) { return fe
 
 extern "C" int cslam_frontend_sync(cslam_frontend* fe) {
     if (!fe) return CSLAM_E_BADARG;
+    CSLAM_CUDA(cudaSetDevice(fe->device));
     CSLAM_CUDA(cudaMemcpyAsync(fe->h_pin_err, fe->d_err, sizeof(int), cudaMemcpyDeviceToHost, fe->stream));
     CSLAM_CUDA(cudaStreamSynchronize(fe->stream));
     if (fe->timing) collect_timing(fe);
@@ -1234,9 +1235,11 @@ static int run_host(cslam_frontend* fe, const uint8_t* in, size_t inFrameBytes, 
     const bool pinIn = is_pinned(in), pinK = is_pinned(kps), pinD = is_pinned(desc), pinN = is_pinned(n_out);
     const size_t nk = (size_t)fe->kpCap;
     if ((rc = fork_lanes(fe, nlanes))) return rc;
-    for (int ck = 0; ck < nchunks; ck++) {
+    // errors inside the loop leave through join_lanes: a lane that was forked is always joined before this function returns
+    auto chunk = [&](int ck) -> int {
+        int rc = 0;
         const int f0 = (int)((long long)batch * ck / nchunks), f1 = (int)((long long)batch * (ck + 1) / nchunks), cnt = f1 - f0;
-        if (cnt <= 0) continue;
+        if (cnt <= 0) return 0;
         cudaStream_t st = fe->lane[ck % nlanes];
         if (fromWarp) {
             const uint8_t* src = in + (size_t)f0 * inFrameBytes;
@@ -1253,8 +1256,13 @@ static int run_host(cslam_frontend* fe, const uint8_t* in, size_t inFrameBytes, 
         CSLAM_CUDA(cudaMemcpyAsync((pinK ? kps : fe->h_pin_kps) + (size_t)f0 * nk, fe->d_kps + (size_t)f0 * nk, (size_t)cnt * nk * sizeof(cslam_keypoint), cudaMemcpyDeviceToHost, st));
         CSLAM_CUDA(cudaMemcpyAsync((pinD ? desc : fe->h_pin_desc) + (size_t)f0 * nk * 32, fe->d_desc + (size_t)f0 * nk * 32, (size_t)cnt * nk * 32, cudaMemcpyDeviceToHost, st));
         CSLAM_CUDA(cudaMemcpyAsync((pinN ? n_out : fe->h_pin_n) + f0, fe->d_nout + f0, (size_t)cnt * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
-    }
-    if ((rc = join_lanes(fe, nlanes))) return rc;
+        return 0;
+    };
+    int erc = 0;
+    for (int ck = 0; ck < nchunks && !erc; ck++) erc = chunk(ck);
+    rc = join_lanes(fe, nlanes);
+    if (erc) { cudaStreamSynchronize(fe->stream); return erc; }
+    if (rc) return rc;
     fe->lastBatch = batch;
     if ((rc = cslam_frontend_sync(fe))) return rc;
     const size_t tot = (size_t)batch * nk;
@@ -1286,14 +1294,16 @@ extern "C" int cslam_frontend_run_dev(cslam_frontend* fe, const uint8_t* fisheye
     const int nlanes = lanes_for(fe, batch, fe->devLanes);
     const size_t nk = (size_t)fe->kpCap, fsz = (size_t)fe->cam.Iw * fe->cam.Ih;
     if ((rc = fork_lanes(fe, nlanes))) return rc;
-    for (int ln = 0; ln < nlanes; ln++) {
+    int erc = 0;
+    for (int ln = 0; ln < nlanes && !erc; ln++) {
         const int f0 = (int)((long long)batch * ln / nlanes), f1 = (int)((long long)batch * (ln + 1) / nlanes), cnt = f1 - f0;
         if (cnt <= 0) continue;
-        if ((rc = launch_warp(fe, fe->lane[ln], fisheye_dev + (size_t)f0 * fsz, f0, cnt))) return rc;
-        if ((rc = launch_extract(fe, fe->lane[ln], f0, cnt, kps_dev + (size_t)f0 * nk, desc_dev + (size_t)f0 * nk * 32, n_out_dev + f0, true))) return rc;
+        if ((erc = launch_warp(fe, fe->lane[ln], fisheye_dev + (size_t)f0 * fsz, f0, cnt))) break;
+        erc = launch_extract(fe, fe->lane[ln], f0, cnt, kps_dev + (size_t)f0 * nk, desc_dev + (size_t)f0 * nk * 32, n_out_dev + f0, true);
     }
     fe->lastBatch = batch;
-    return join_lanes(fe, nlanes);
+    rc = join_lanes(fe, nlanes);   // forked lanes are joined on the error path too
+    return erc ? erc : rc;
 }
 
 extern "C" int cslam_frontend_level_size(const cslam_frontend* fe, int level, int* w, int* h) {
