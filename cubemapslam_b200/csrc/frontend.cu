@@ -655,7 +655,8 @@ struct DescribeArgs {
 };
 
 static const int DP_STRIDE = 48;                 // patch row stride (bytes): 43 px + up to 3 bytes of word misalignment
-static const int DH_STRIDE = 44;                 // transposed H: u16 per row index, per column
+static const int DH_STRIDE = 46;                 // transposed H: u16 per row index, per column (23 words: the 4-column stride of the transposed stores, 92 words, spreads over 8 banks)
+static const int BL_STRIDE = 44;                 // blurred patch row stride in bytes (11 words: 4-row stride 44 words -> 8 banks; 40 gave 4)
 __global__ void __launch_bounds__(DESC_WARPS * 32) k_describe(DescribeArgs A) {
     __shared__ __align__(16) uint8_t s_patch[DESC_WARPS][43 * DP_STRIDE + 16];
     __shared__ __align__(16) uint16_t s_ht[DESC_WARPS][37 * DH_STRIDE + 8];
@@ -750,7 +751,7 @@ __global__ void __launch_bounds__(DESC_WARPS * 32) k_describe(DescribeArgs A) {
             o[2] = __dp2a_lo(q1, K01, __dp2a_lo(q2, K23, __dp2a_lo(q3, K45, 18u * (q4 & 0xffffu))));
             o[3] = __dp2a_lo(s12, K01, __dp2a_lo(s23, K23, __dp2a_lo(s34, K45, 18u * (q4 >> 16))));
 #pragma unroll
-            for (int j = 0; j < 4; j++) if (4 * rg + j < 37) Bl[(4 * rg + j) * 40 + c] = (uint8_t)((o[j] + 32768u) >> 16);
+            for (int j = 0; j < 4; j++) if (4 * rg + j < 37) Bl[(4 * rg + j) * BL_STRIDE + c] = (uint8_t)((o[j] + 32768u) >> 16);
         }
     }
     __syncwarp();
@@ -765,7 +766,7 @@ __global__ void __launch_bounds__(DESC_WARPS * 32) k_describe(DescribeArgs A) {
         const float x0 = (float)pat[4 * k], y0 = (float)pat[4 * k + 1], x1 = (float)pat[4 * k + 2], y1 = (float)pat[4 * k + 3];
         const int r0 = __float2int_rn(__fadd_rn(__fmul_rn(x0, b), __fmul_rn(y0, a))), c0 = __float2int_rn(__fsub_rn(__fmul_rn(x0, a), __fmul_rn(y0, b)));
         const int r1 = __float2int_rn(__fadd_rn(__fmul_rn(x1, b), __fmul_rn(y1, a))), c1 = __float2int_rn(__fsub_rn(__fmul_rn(x1, a), __fmul_rn(y1, b)));
-        const int t0 = Bl[(r0 + 18) * 40 + c0 + 18], t1 = Bl[(r1 + 18) * 40 + c1 + 18];
+        const int t0 = Bl[(r0 + 18) * BL_STRIDE + c0 + 18], t1 = Bl[(r1 + 18) * BL_STRIDE + c1 + 18];
         val |= (uint32_t)(t0 < t1) << k;
     }
     A.desc[((size_t)frame * A.kpCap + outIdx) * 32 + lane] = (uint8_t)val;
