@@ -5,7 +5,7 @@ Mirrors what System / Tracking read (reference src/System.cpp:63-91, src/Trackin
 """
 import os
 
-_FIXTURES = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "fixtures")
+_FIXTURES = os.path.join(os.path.dirname(os.path.abspath(__file__)), "data")   # camera parameters + bit-packed cube masks of the reference settings
 
 
 def load_settings(path, **overrides):
@@ -33,7 +33,7 @@ def fixture(name):
 
 
 def camera(name, **overrides):
-    """Parameters of one of the reference's settings files (tests/fixtures/cameras.json holds the values of
+    """Parameters of one of the reference's settings files (cubemapslam_b200/data/cameras.json holds the values of
     Config/{lafida_cam0,front_cam,left_cam}_params.yaml under the reference's own key names)."""
     import json
     cfg = dict(json.load(open(fixture("cameras.json")))["cameras"][name])
@@ -44,7 +44,7 @@ def camera(name, **overrides):
 
 def load_mask(name):
     """Binary cubemap mask (0/255, uint8) shipped by the reference under Masks/<name>.png, stored bit-packed in
-    tests/fixtures/cubemap_masks.npz."""
+    cubemapslam_b200/data/cubemap_masks.npz."""
     import numpy as np
     z = np.load(fixture("cubemap_masks.npz"))
     h, w = (int(v) for v in z[name + "_shape"])
