@@ -29,10 +29,10 @@ static const int FAST_TS = 208;     // smem tile stride (bytes), >= CG*CELL_MAX+
 static const int FAST_TH = CELL_MAX + 6;
 static const int DESC_WARPS = 4;
 
-__constant__ signed char c_pattern[1024] = {
-#include "brief_pattern.inc"
-};
 __constant__ int c_umax[16];
+// the BRIEF pattern as k_describe reads it: word k of lane (= output byte) `lane` at [k * 32 + lane] (coalesced; the byte-per-test table above
+// read per lane was an 8-way shared-memory bank conflict). Filled by cslam_frontend_create from the same table.
+__device__ uint32_t g_patT[8 * 32];
 
 struct LevelGeom {
     int w, h, pitch;          // image size, row pitch in bytes
@@ -654,17 +654,14 @@ struct DescribeArgs {
     int* errFlag;
 };
 
-static const int DP_STRIDE = 48;                 // patch row stride (bytes): 43 px + up to 3 bytes of word misalignment
+static const int DP_STRIDE = 52;                 // patch row stride (bytes): 43 px + up to 3 bytes of word misalignment; 13 words: consecutive rows fall in distinct banks
 static const int DH_STRIDE = 46;                 // transposed H: u16 per row index, per column (23 words: the 4-column stride of the transposed stores, 92 words, spreads over 8 banks)
 static const int BL_STRIDE = 44;                 // blurred patch row stride in bytes (11 words: 4-row stride 44 words -> 8 banks; 40 gave 4)
 __global__ void __launch_bounds__(DESC_WARPS * 32) k_describe(DescribeArgs A) {
     __shared__ __align__(16) uint8_t s_patch[DESC_WARPS][43 * DP_STRIDE + 16];
     __shared__ __align__(16) uint16_t s_ht[DESC_WARPS][37 * DH_STRIDE + 8];
-    __shared__ signed char s_pat[1024];
     const int level = blockIdx.y, frame = blockIdx.z;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    for (int i = threadIdx.x; i < 1024; i += blockDim.x) s_pat[i] = c_pattern[i];
-    __syncthreads();
     const uint32_t* kc = A.keptCount + (size_t)frame * A.L.nlevels;
     const int slot = blockIdx.x * DESC_WARPS + warp;
     int offset = 0, total = 0;
@@ -719,8 +716,8 @@ __global__ void __launch_bounds__(DESC_WARPS * 32) k_describe(DescribeArgs A) {
     uint16_t* Ht = s_ht[warp];
     {
         const uint32_t K0123 = 18u | (34u << 8) | (48u << 16) | (56u << 24), K456 = 48u | (34u << 8) | (18u << 16);
-        for (int it = lane; it < 43 * 10; it += 32) {
-            const int r = it / 10, cg = it - r * 10;
+        for (int it = lane; it < 43 * 10; it += 32) {   // lanes = consecutive rows of one column group: loads 13 words apart, transposed stores contiguous
+            const int cg = it / 43, r = it - cg * 43;
             const int bidx = po + 4 * cg;
             const uint32_t* W = reinterpret_cast<const uint32_t*>(P + r * DP_STRIDE) + (bidx >> 2);
             const int sh = (bidx & 3) * 8;
@@ -740,8 +737,8 @@ __global__ void __launch_bounds__(DESC_WARPS * 32) k_describe(DescribeArgs A) {
     uint8_t* Bl = s_patch[warp];   // the raw patch is dead after the horizontal pass
     {
         const uint32_t K01 = 18u | (34u << 8), K23 = 48u | (56u << 8), K45 = 48u | (34u << 8);
-        for (int it = lane; it < 37 * 10; it += 32) {
-            const int c = it / 10, rg = it - c * 10;
+        for (int it = lane; it < 37 * 10; it += 32) {   // lanes = consecutive columns of one row group: loads 23 words apart, byte stores contiguous
+            const int rg = it / 37, c = it - rg * 37;
             const uint32_t* Hw = reinterpret_cast<const uint32_t*>(Ht + c * DH_STRIDE) + 2 * rg;
             const uint32_t q0 = Hw[0], q1 = Hw[1], q2 = Hw[2], q3 = Hw[3], q4 = Hw[4];
             const uint32_t s01 = __funnelshift_r(q0, q1, 16), s12 = __funnelshift_r(q1, q2, 16), s23 = __funnelshift_r(q2, q3, 16), s34 = __funnelshift_r(q3, q4, 16);
@@ -759,11 +756,12 @@ __global__ void __launch_bounds__(DESC_WARPS * 32) k_describe(DescribeArgs A) {
     const float factorPI = (float)(3.14159265358979323846 / 180.0);
     float a, b;
     det_sincosf(__fmul_rn(angle, factorPI), &b, &a);
-    const signed char* pat = s_pat + lane * 32;
     uint32_t val = 0;
 #pragma unroll
     for (int k = 0; k < 8; k++) {
-        const float x0 = (float)pat[4 * k], y0 = (float)pat[4 * k + 1], x1 = (float)pat[4 * k + 2], y1 = (float)pat[4 * k + 3];
+        const uint32_t pw = __ldg(g_patT + k * 32 + lane);
+        const float x0 = (float)(int)(signed char)(pw & 0xff), y0 = (float)(int)(signed char)((pw >> 8) & 0xff), x1 = (float)(int)(signed char)((pw >> 16) & 0xff),
+                    y1 = (float)(int)(signed char)(pw >> 24);
         const int r0 = __float2int_rn(__fadd_rn(__fmul_rn(x0, b), __fmul_rn(y0, a))), c0 = __float2int_rn(__fsub_rn(__fmul_rn(x0, a), __fmul_rn(y0, b)));
         const int r1 = __float2int_rn(__fadd_rn(__fmul_rn(x1, b), __fmul_rn(y1, a))), c1 = __float2int_rn(__fsub_rn(__fmul_rn(x1, a), __fmul_rn(y1, b)));
         const int t0 = Bl[(r0 + 18) * BL_STRIDE + c0 + 18], t1 = Bl[(r1 + 18) * BL_STRIDE + c1 + 18];
@@ -942,6 +940,18 @@ extern "C" int cslam_frontend_create(cslam_frontend** out, int device, const csl
     if (const char* e = getenv("CSLAM_DEV_LANES")) fe->devLanes = std::max(1, std::min(atoi(e), (int)cslam_frontend::MAX_LANES));
     if (const char* e = getenv("CSLAM_HOST_CHUNKS")) fe->hostChunks = std::max(1, std::min(atoi(e), 64));
     if (cudaMemcpyToSymbol(c_umax, fe->umax, sizeof(fe->umax)) != cudaSuccess) { set_error("cudaMemcpyToSymbol failed"); return fail(CSLAM_E_CUDA); }
+    {
+        static const signed char hostPattern[1024] = {
+#include "brief_pattern.inc"
+        };
+        uint32_t patT[8 * 32];
+        for (int ln = 0; ln < 32; ln++)
+            for (int k = 0; k < 8; k++) {
+                const unsigned char* q = reinterpret_cast<const unsigned char*>(hostPattern) + ln * 32 + 4 * k;
+                patT[k * 32 + ln] = (uint32_t)q[0] | ((uint32_t)q[1] << 8) | ((uint32_t)q[2] << 16) | ((uint32_t)q[3] << 24);
+            }
+        if (cudaMemcpyToSymbol(g_patT, patT, sizeof(patT)) != cudaSuccess) { set_error("cudaMemcpyToSymbol failed"); return fail(CSLAM_E_CUDA); }
+    }
     // ---- level geometry (ComputePyramid :930-936, ComputeKeyPointsOctTree :747-761)
     std::memset(&fe->L, 0, sizeof(fe->L));
     fe->L.nlevels = nl;
