@@ -227,6 +227,35 @@ int dropin_local_ba(int nKF, int nMP, int nE, float* Tcw, float* pts, const int3
 }
 
 
+// Optimizer::GlobalBundleAdjustemnt(pMap, nIterations, NULL, 0, true) (src/Tracking.cpp:514 after map initialisation, src/LoopClosing.cpp:649) on a Map built
+// with the reference's API: all key frames / MapPoints, one optimize(nIterations), poses / points written back through SetPose / SetWorldPos.
+void dropin_global_ba(int nKF, int nMP, int nE, float* Tcw, float* pts, const int32_t* eMP, const int32_t* eKF, const float* kpxy, const int32_t* octave, int nIterations) {
+    KeyFrame::nNextId = 0; MapPoint::nNextId = 0;
+    Map* map = new Map();
+    std::vector<std::vector<int> > edgesOfKF(nKF);
+    for (int e = 0; e < nE; e++) edgesOfKF[eKF[e]].push_back(e);
+    std::vector<KeyFrame*> kfs(nKF); std::vector<int> slot(nE);
+    for (int k = 0; k < nKF; k++) {
+        const int n = (int)edgesOfKF[k].size();
+        std::vector<KpPOD> kps(n);
+        for (int i = 0; i < n; i++) { const int e = edgesOfKF[k][i]; slot[e] = i; kps[i].x = kpxy[2 * e]; kps[i].y = kpxy[2 * e + 1]; kps[i].size = 31; kps[i].angle = 0; kps[i].response = 0; kps[i].octave = octave[e]; kps[i].class_id = -1; }
+        Frame* F = make_frame(n, kps.data(), NULL, Tcw + 16 * k, 8, 1.2f);
+        kfs[k] = new KeyFrame(*F, map, NULL);
+        map->AddKeyFrame(kfs[k]);
+        delete F;
+    }
+    std::vector<MapPoint*> mps(nMP, static_cast<MapPoint*>(NULL));
+    for (int e = 0; e < nE; e++) {
+        const int l = eMP[e];
+        if (!mps[l]) { mps[l] = new MapPoint(mat_from(pts + 3 * l, 3, 1), kfs[eKF[e]], map); map->AddMapPoint(mps[l]); }
+    }
+    for (int l = 0; l < nMP; l++) if (!mps[l]) { mps[l] = new MapPoint(mat_from(pts + 3 * l, 3, 1), kfs[0], map); }
+    for (int e = 0; e < nE; e++) { mps[eMP[e]]->AddObservation(kfs[eKF[e]], slot[e]); kfs[eKF[e]]->AddMapPoint(mps[eMP[e]], slot[e]); }
+    Optimizer::GlobalBundleAdjustemnt(map, nIterations, NULL, 0, true);      // dropin/Optimizer_b200.cpp
+    for (int k = 0; k < nKF; k++) { const cv::Mat T = kfs[k]->GetPose(); for (int r = 0; r < 4; r++) for (int c = 0; c < 4; c++) Tcw[16 * k + 4 * r + c] = T.at<float>(r, c); }
+    for (int l = 0; l < nMP; l++) { const cv::Mat P = mps[l]->GetWorldPos(); for (int c = 0; c < 3; c++) pts[3 * l + c] = P.at<float>(c); }
+}
+
 // ORBMatcher(0.6).Fuse(pKF, vpMapPoints, th) (LocalMapping::SearchInNeighbors): the GPU drop-in and the reference's own CPU body on identical object
 // graphs (a key frame without MapPoints; MapPoint m observed once, by key point m of a second key frame). idx*[m] = key point of pKF on which the
 // MapPoint (or what replaced it) sits afterwards, -1 none; bad*[m] = isBad(). nFused by return values.

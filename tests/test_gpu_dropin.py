@@ -202,3 +202,31 @@ def test_batched_distinctive_descriptors_on_reference_map_points(oracle):
     L.dropin_distinctive_batch(P, _p(off), _p(desc), _p(eq))
     assert eq.all()
     L.dropin_set_camera(C.byref(oracle.cam_params(config.lafida_450())))
+
+
+def test_global_bundle_adjustment_on_reference_map(oracle, dropin):
+    """Optimizer::GlobalBundleAdjustemnt(pMap, 20) (src/Tracking.cpp:514, src/LoopClosing.cpp:649; body src/Optimizer.cpp:461-621) through the drop-in on a
+    Map built with the reference's API == the oracle's LM with one optimize(20), robust kernel on, no outlier stage."""
+    L, cfg, cp = dropin
+    p = synth.ba_problem(nKF=7, nMP=350, kmin=3, kmax=7, faceW=450, seed=31, radius=1.5)
+    kp0 = np.zeros(len(p["eMP"]), KP); kp0["x"] = p["kpxy"][:, 0]; kp0["y"] = p["kpxy"][:, 1]
+    rays, _ = oracle.key_point_rays(kp0, 450, 450)
+    a = np.float32(cfg["Camera.fov"]) / np.float32(2) * (np.float32(3.1415926535897932384626) / np.float32(180))
+    keep = rays[:, 2] >= np.float32(np.cos(np.float64(a)))       # the reference skips observations outside the field of view (src/Optimizer.cpp:520)
+    for key in ("eMP", "eKF", "kpxy", "inv_sigma2"):
+        p[key] = np.ascontiguousarray(p[key][keep])
+    nKF, nMP, nE = 7, 350, len(p["eMP"])
+    rng = np.random.default_rng(4)
+    octave = rng.integers(0, 8, nE).astype(np.int32)
+    sc = np.float32(1.0); tab = []
+    for i in range(8):
+        tab.append(np.float32(1.0) / (sc * sc)); sc = sc * np.float32(1.2)
+    inv_sigma2 = np.array([tab[o] for o in octave], np.float32)
+    T = np.ascontiguousarray(p["Tcw"], np.float32).reshape(nKF, 16).copy(); pts = np.ascontiguousarray(p["pts"], np.float32).copy()
+    L.dropin_global_ba(nKF, nMP, nE, _p(T), _p(pts), _p(p["eMP"]), _p(p["eKF"]), _p(np.ascontiguousarray(p["kpxy"], np.float32)), _p(octave), 20)
+    fixed = np.zeros(nKF, np.uint8); fixed[0] = 1                 # only mnId == 0 is fixed
+    r = oracle.local_ba(p["Tcw"], fixed, p["pts"], p["eMP"], p["eKF"], p["kpxy"], inv_sigma2, 450, 450, its1=20, its2=0)
+    assert r["iters"] >= 5
+    seen = np.bincount(p["eMP"], minlength=nMP) > 0
+    assert np.allclose(T.reshape(nKF, 4, 4), r["Tcw"], atol=2e-6) and np.allclose(pts[seen], r["pts"][seen], atol=2e-6)
+    assert not np.allclose(T.reshape(nKF, 4, 4)[1:], p["Tcw"][1:], atol=1e-4)      # it did move the free key frames
