@@ -126,9 +126,8 @@ def run_ours(args):
     dev = torch.device("cuda", local)
     if world > 1:
         import torch.distributed as dist
-        # NCCL prints its version banner on stdout at NCCL_DEBUG=VERSION (this image's default): stdout carries the one JSON line only
-        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
-            os.environ["NCCL_DEBUG"] = "WARN"
+        # NCCL writes its version banner (NCCL_DEBUG >= VERSION, set in this image) to stdout: send NCCL's log to stderr, stdout carries the one JSON line only
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=dev)
     cfg = config.front_1024()
     mask = load_mask()
