@@ -322,7 +322,7 @@ def run_ours(args):
            "e2e": {"value": round(e2e_value, 1), "unit": "frames/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                    "frames_per_step": ef, "steps": args.e2e_steps, "calls": "cslam_frontend_run + cslam_match_frames (host buffers); the matcher call of batch i runs on a second host thread while the front-end call of batch i+1 runs"},
            "roofline": roof, "cpu_baseline": cpu, "extra": extra}
-    print(json.dumps(out))
+    emit(out)
     if world > 1:
         dist.destroy_process_group()
 
@@ -442,10 +442,33 @@ def run_reference(args):
            "warmup": args.warmup, "ms_per_step": round(1e3 * c["seconds"], 1), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8",
            "data": "synthetic", "config": {"workload": "configs[1]+[2]: warp + ORB extract + consecutive-frame match, 1280x1024 frames, 650-px faces, nFeatures 3000 (bounded sample of 192 frames per step)"},
            "cpu_baseline": c, "e2e": {"value": round(v, 2), "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(out))
+    emit(out)
+
+
+_RESULT_FD = None
+
+
+def _claim_stdout():
+    """stdout must carry exactly one JSON line. Libraries below us write there too (NCCL prints its version banner on stdout in this image,
+    whatever NCCL_DEBUG_FILE says), so file descriptor 1 is pointed at stderr for the whole run and the result line goes to a private duplicate
+    of the original stdout."""
+    global _RESULT_FD
+    if _RESULT_FD is None:
+        sys.stdout.flush()
+        _RESULT_FD = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(obj):
+    line = (json.dumps(obj) + "\n").encode()
+    if _RESULT_FD is None:
+        sys.stdout.write(line.decode()); sys.stdout.flush()
+    else:
+        os.write(_RESULT_FD, line)
 
 
 def main():
+    _claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=3)
