@@ -32,3 +32,19 @@ def test_dropin_signatures_are_the_reference_declarations():
     for src in glob.glob(os.path.join(ROOT, "dropin", "*.cpp")):
         txt = open(src).read()
         assert not re.search(r"^\s*(class|struct)\s+(ORBMatcher|Optimizer|ORBextractor|System)\b", txt, flags=re.M), src
+
+
+def test_integration_doc_names_the_renames_the_recipe_uses():
+    """INTEGRATION.md tells a maintainer which reference bodies to rename away per file; oracle/Makefile builds libdropin.so with exactly those
+    definitions. The two must not drift apart (a missing rename = a duplicate symbol at link time in the maintainer's tree)."""
+    mk = open(os.path.join(ROOT, "oracle", "Makefile")).read()
+    doc = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    m = re.search(r"^RENAME := (.*)$", mk, flags=re.M)
+    assert m
+    renames = re.findall(r"-D(\w+=\w+)", m.group(1))
+    assert len(renames) >= 4
+    for r in renames:
+        assert r in doc, r
+    # every drop-in source the recipe links is listed in the CMake snippet
+    for src in sorted(glob.glob(os.path.join(ROOT, "dropin", "*_b200.cpp"))):
+        assert os.path.basename(src) in doc, src
