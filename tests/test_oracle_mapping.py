@@ -72,3 +72,28 @@ def test_search_for_triangulation(oracle, cam, seed, ori):
     assert np.array_equal(m1, m2)
     good = m1 >= 0
     assert (s["src"][good] == m1[good]).mean() > 0.9
+
+
+def test_fuse_on_face_boundaries(oracle, cam):
+    """TransformRaysToCubemap leaves in-face coordinates (no tile offset) in (u, v) when its in-face bounds test fails, and Fuse does not look at the
+    returned face - it only asks IsInImage(u, v) (src/ORBMatcher.cpp:1150-1154). MapPoints exactly on a face seam (|x/z| == 1 etc.) and behind the
+    camera exercise that path: oracle == compiled reference."""
+    cp, r = cam
+    s = synth.mapping_pair(5, n=1200, faceW=650)
+    rng = np.random.default_rng(11)
+    Xw = s["Xw"].copy()
+    n = len(Xw)
+    d = rng.uniform(2.0, 9.0, n).astype(np.float32); y = rng.uniform(-0.9, 0.9, n).astype(np.float32) * d
+    k = np.arange(n) % 6
+    Xw[k == 0] = np.stack([d, y, d], 1)[k == 0]           # x / z == 1: front test passes, u == W fails the in-face test
+    Xw[k == 1] = np.stack([-d, y, d], 1)[k == 1]          # x / z == -1
+    Xw[k == 2] = np.stack([y, d, d], 1)[k == 2]           # y / z == 1
+    Xw[k == 3] = np.stack([d, y, -d], 1)[k == 3]          # behind: right face, z / x == -1
+    Xw[k == 4] = 0                                        # the origin: no face at all -> (-1, -1)
+    I4 = np.eye(4, dtype=np.float32)
+    nf, valid, level, idx = r.fuse(s["kCur"], s["dCur"], I4, Xw, s["kLast"], s["dLast"], I4, 4.0)
+    g = oracle.FrameGrid(s["kCur"], 650, 650)
+    bi, bd = g.fuse_search(s["dCur"], I4, s["scale"], s["inv_level_sigma2"], valid, Xw, level, s["dLast"], 4.0)
+    fused = bd <= 50
+    assert nf == int(fused.sum())
+    assert np.array_equal(np.where(fused, bi, -1), idx)
